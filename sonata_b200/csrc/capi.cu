@@ -1,0 +1,302 @@
+// extern "C" surface of libsonata_b200 (declared in include/sonata_b200.h).
+// Error handling mirrors ffi_support::call_with_result used by libsonata (capi/src/lib.rs:187-336):
+// no exception crosses the ABI; failures become {code, heap message}.
+#include "../../include/sonata_b200.h"
+#include "engine.h"
+#include <chrono>
+#include <cstring>
+#include <deque>
+
+using namespace sb200;
+
+struct sb200_voice { Voice* v; };
+struct sb200_job { Job* j; };
+struct sb200_latent { Latent* l; };
+
+namespace {
+
+// ---- pinned result blocks, shared by the sb200_audio entries of one batch and recycled ----
+struct PinnedBlock { std::atomic<int> refs{0}; float* base = nullptr; size_t bytes = 0; };
+std::mutex g_pin_mu;
+std::deque<PinnedBlock*> g_pin_free;
+std::unordered_map<const float*, PinnedBlock*> g_owner;   // audio.data -> block
+
+PinnedBlock* pin_acquire(size_t bytes) {
+    {
+        std::lock_guard<std::mutex> g(g_pin_mu);
+        for (auto it = g_pin_free.begin(); it != g_pin_free.end(); ++it)
+            if ((*it)->bytes >= bytes && (*it)->bytes <= 2 * bytes + (1 << 20)) {
+                PinnedBlock* b = *it;
+                g_pin_free.erase(it);
+                return b;
+            }
+    }
+    PinnedBlock* b = new PinnedBlock();
+    b->bytes = bytes + bytes / 8 + 4096;
+    void* p = nullptr;
+    if (cudaMallocHost(&p, b->bytes) != cudaSuccess) { delete b; throw Error(19, "cudaMallocHost failed for the result buffer"); }
+    b->base = (float*)p;
+    return b;
+}
+void pin_release(PinnedBlock* b) {
+    std::lock_guard<std::mutex> g(g_pin_mu);
+    if (g_pin_free.size() >= 4) { cudaFreeHost(b->base); delete b; return; }
+    g_pin_free.push_back(b);
+}
+
+char* dup_cstr(const std::string& s) {
+    char* p = (char*)malloc(s.size() + 1);
+    if (p) memcpy(p, s.c_str(), s.size() + 1);
+    return p;
+}
+
+template <typename F>
+int32_t guarded(sb200_error* err, F&& f) {
+    if (err) { err->code = 0; err->message = nullptr; }
+    try {
+        f();
+        return 0;
+    } catch (const Error& e) {
+        if (err) { err->code = e.code; err->message = dup_cstr(e.what()); }
+        return e.code;
+    } catch (const std::exception& e) {
+        if (err) { err->code = 19; err->message = dup_cstr(e.what()); }
+        return 19;
+    } catch (...) {
+        if (err) { err->code = -1; err->message = dup_cstr("panic"); }
+        return -1;
+    }
+}
+
+void fetch_audio(Job& j, sb200_audio* outs, float wall_ms) {
+    if (!j.ran || j.encode_only) throw Error(19, "job has not produced audio");
+    Voice& v = *j.v;
+    SB_CUDA(cudaSetDevice(v.device));
+    PinnedBlock* blk = pin_acquire((size_t)j.total_samples * 4 + 16);
+    cudaError_t e = cudaMemcpyAsync(blk->base, j.d_wav, (size_t)j.total_samples * 4, cudaMemcpyDeviceToHost, j.ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(j.ctx->stream);
+    if (e != cudaSuccess) { pin_release(blk); throw Error(19, std::string("CUDA error: ") + cudaGetErrorString(e)); }
+    blk->refs = (int)j.B;
+    const int hop = v.a.hop();
+    std::lock_guard<std::mutex> g(g_pin_mu);
+    for (size_t b = 0; b < j.B; b++) {
+        outs[b].data = blk->base + j.fsegs[b].out_off;
+        outs[b].len = (size_t)j.y_len[b] * hop;
+        outs[b].sample_rate = (uint32_t)v.sample_rate;
+        outs[b].inference_ms = wall_ms * (j.total_samples ? (float)outs[b].len / (float)j.total_samples : 0.f);
+        g_owner[outs[b].data] = blk;
+    }
+}
+
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* sb200_version(void) { return "sonata_b200 0.1.0 (sm_100a)"; }
+void sb200_string_free(char* s) { free(s); }
+void sb200_ids_free(int64_t* ids) { free(ids); }
+void sb200_buffer_free(float* p) { free(p); }
+int32_t sb200_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
+
+void sb200_audio_free(sb200_audio* a) {
+    if (!a || !a->data) return;
+    PinnedBlock* blk = nullptr;
+    {
+        std::lock_guard<std::mutex> g(g_pin_mu);
+        auto it = g_owner.find(a->data);
+        if (it != g_owner.end()) { blk = it->second; g_owner.erase(it); }
+    }
+    if (blk) { if (--blk->refs == 0) pin_release(blk); }
+    else free(a->data);
+    a->data = nullptr; a->len = 0;
+}
+
+int32_t sb200_voice_load(const char* config_path, int32_t device, sb200_voice** out, sb200_error* err) {
+    return guarded(err, [&] {
+        if (!config_path || !out) throw Error(19, "null argument");
+        Voice* v = load_voice(config_path, device);
+        *out = new sb200_voice{v};
+    });
+}
+void sb200_voice_free(sb200_voice* v) { if (v) { delete v->v; delete v; } }
+
+int32_t sb200_audio_output_info(const sb200_voice* v, sb200_audio_info* out, sb200_error* err) {
+    return guarded(err, [&] {
+        out->sample_rate = (uint32_t)v->v->sample_rate; out->num_channels = 1; out->sample_width = 2;
+    });
+}
+
+static void cfg_out(const SynthConfig& c, sb200_synth_config* o) {
+    o->speaker = c.speaker; o->has_speaker = c.has_speaker ? 1 : 0;
+    o->noise_scale = c.noise_scale; o->length_scale = c.length_scale; o->noise_w = c.noise_w;
+}
+int32_t sb200_get_default_synthesis_config(const sb200_voice* v, sb200_synth_config* out, sb200_error* err) {
+    return guarded(err, [&] {   // always Some(0), piper/src/lib.rs:444-451
+        SynthConfig c = v->v->factory_cfg; c.speaker = 0; c.has_speaker = true; cfg_out(c, out);
+    });
+}
+int32_t sb200_get_fallback_synthesis_config(const sb200_voice* v, sb200_synth_config* out, sb200_error* err) {
+    return guarded(err, [&] { std::shared_lock<std::shared_mutex> g(v->v->cfg_mu); cfg_out(v->v->cfg, out); });
+}
+int32_t sb200_set_fallback_synthesis_config(sb200_voice* v, const sb200_synth_config* c, sb200_error* err) {
+    return guarded(err, [&] {   // _do_set_default_synth_config, piper/src/lib.rs:215-231
+        std::unique_lock<std::shared_mutex> g(v->v->cfg_mu);
+        v->v->cfg.length_scale = c->length_scale; v->v->cfg.noise_scale = c->noise_scale; v->v->cfg.noise_w = c->noise_w;
+        if (c->has_speaker) {
+            bool found = false;
+            for (auto& kv : v->v->speaker_id_map) if (kv.second == c->speaker) found = true;
+            if (!found) throw Error(19, "No speaker was found with the given id `" + std::to_string(c->speaker) + "`");
+            v->v->cfg.speaker = c->speaker; v->v->cfg.has_speaker = true;
+        }
+    });
+}
+int32_t sb200_get_language(const sb200_voice* v, char** out, sb200_error* err) {
+    return guarded(err, [&] { *out = dup_cstr(v->v->language_code.empty() ? v->v->espeak_voice : v->v->language_code); });
+}
+int32_t sb200_get_quality(const sb200_voice* v, char** out, sb200_error* err) {
+    return guarded(err, [&] { *out = dup_cstr(v->v->quality.empty() ? "unknown" : v->v->quality); });
+}
+int32_t sb200_supports_streaming_output(const sb200_voice* v) { return v->v->streaming ? 1 : 0; }
+int32_t sb200_num_speakers(const sb200_voice* v) { return v->v->num_speakers; }
+int64_t sb200_speaker_name_to_id(const sb200_voice* v, const char* name) {
+    auto it = v->v->speaker_id_map.find(name ? name : "");
+    return it == v->v->speaker_id_map.end() ? -1 : it->second;
+}
+
+int32_t sb200_phonemes_to_input_ids(const sb200_voice* v, const char* ph, int64_t** ids, size_t* n, sb200_error* err) {
+    return guarded(err, [&] {
+        std::vector<long long> r = v->v->phonemes_to_ids(ph);
+        *ids = (int64_t*)malloc(r.size() * sizeof(int64_t));
+        for (size_t i = 0; i < r.size(); i++) (*ids)[i] = r[i];
+        *n = r.size();
+    });
+}
+
+int32_t sb200_speak_batch_ids(sb200_voice* v, const int64_t* ids, const size_t* offsets, size_t batch,
+                              sb200_audio* outs, sb200_error* err) {
+    return guarded(err, [&] {
+        const double t0 = now_ms();
+        static_assert(sizeof(long long) == sizeof(int64_t), "");
+        std::unique_ptr<Job> j(create_job(v->v, reinterpret_cast<const long long*>(ids), offsets, batch, nullptr,
+                                          nullptr, nullptr, false));
+        j->run(nullptr, 0);
+        fetch_audio(*j, outs, 0.f);
+        const float wall = (float)(now_ms() - t0);
+        for (size_t b = 0; b < batch; b++)
+            outs[b].inference_ms = wall * (j->total_samples ? (float)outs[b].len / (float)j->total_samples : 0.f);
+    });
+}
+int32_t sb200_speak_ids(sb200_voice* v, const int64_t* ids, size_t n, sb200_audio* out, sb200_error* err) {
+    const size_t offs[2] = {0, n};
+    return sb200_speak_batch_ids(v, ids, offs, 1, out, err);
+}
+int32_t sb200_speak_batch(sb200_voice* v, const char* const* ph, size_t batch, sb200_audio* outs, sb200_error* err) {
+    std::vector<int64_t> ids; std::vector<size_t> offs{0};
+    int32_t rc = guarded(err, [&] {
+        for (size_t b = 0; b < batch; b++) {
+            std::vector<long long> r = v->v->phonemes_to_ids(ph[b]);
+            ids.insert(ids.end(), r.begin(), r.end());
+            offs.push_back(ids.size());
+        }
+    });
+    if (rc) return rc;
+    return sb200_speak_batch_ids(v, ids.data(), offs.data(), batch, outs, err);
+}
+int32_t sb200_speak_one_sentence(sb200_voice* v, const char* ph, sb200_audio* out, sb200_error* err) {
+    return sb200_speak_batch(v, &ph, 1, out, err);
+}
+
+// ---- job API ----
+int32_t sb200_job_create(sb200_voice* v, const int64_t* ids, const size_t* offsets, size_t batch,
+                         const float* const* eps_w, const float* const* eps_z, const size_t* eps_z_frames,
+                         sb200_job** out, sb200_error* err) {
+    return guarded(err, [&] {
+        Job* j = create_job(v->v, reinterpret_cast<const long long*>(ids), offsets, batch, eps_w, eps_z, eps_z_frames, false);
+        *out = new sb200_job{j};
+    });
+}
+int32_t sb200_job_set_debug(sb200_job* job, int32_t on) { job->j->debug = on != 0; return 0; }
+int32_t sb200_job_run(sb200_job* job, float* d_out, size_t cap, float* device_ms, sb200_error* err) {
+    return guarded(err, [&] { job->j->run(d_out, cap); if (device_ms) *device_ms = job->j->last_ms; });
+}
+int32_t sb200_job_fetch(sb200_job* job, sb200_audio* outs, sb200_error* err) {
+    return guarded(err, [&] { fetch_audio(*job->j, outs, job->j->last_ms); });
+}
+size_t sb200_job_batch(const sb200_job* job) { return job->j->B; }
+int32_t sb200_job_lengths(const sb200_job* job, int64_t* frames, int64_t* samples, int64_t* out_offsets) {
+    const Job& j = *job->j;
+    if (!j.ran) return 19;
+    const int hop = j.v->a.hop();
+    for (size_t b = 0; b < j.B; b++) {
+        if (frames) frames[b] = j.y_len[b];
+        if (samples) samples[b] = (int64_t)j.y_len[b] * hop;
+        if (out_offsets) out_offsets[b] = j.fsegs[b].out_off;
+    }
+    return 0;
+}
+void sb200_job_free(sb200_job* job) { if (job) { delete job->j; delete job; } }
+
+// ---- streaming halves ----
+int32_t sb200_encode_ids(sb200_voice* v, const int64_t* ids, size_t n, sb200_latent** out, sb200_error* err) {
+    return guarded(err, [&] { *out = new sb200_latent{encode_latent(v->v, reinterpret_cast<const long long*>(ids), n)}; });
+}
+int64_t sb200_latent_frames(const sb200_latent* z) { return z->l->frames; }
+int32_t sb200_decode_chunk(sb200_voice* v, const sb200_latent* z, int64_t lo, int64_t hi, sb200_audio* out, sb200_error* err) {
+    return guarded(err, [&] {
+        std::vector<float> w; float ms = 0;
+        decode_latent_chunk(v->v, z->l, lo, hi, w, &ms);
+        out->data = (float*)malloc(w.size() * 4 + 4);
+        memcpy(out->data, w.data(), w.size() * 4);
+        out->len = w.size(); out->inference_ms = ms; out->sample_rate = (uint32_t)v->v->sample_rate;
+    });
+}
+void sb200_latent_free(sb200_latent* z) { if (z) { delete z->l; delete z; } }
+
+// ---- introspection ----
+int32_t sb200_job_debug_fetch(sb200_job* job, const char* name, size_t b, float** data, size_t* rows, size_t* cols, sb200_error* err) {
+    return guarded(err, [&] {
+        Job& j = *job->j;
+        auto it = j.dbg.find(name);
+        if (!j.ran || it == j.dbg.end()) throw Error(19, std::string("no debug buffer named `") + name + "` (was debug enabled before run?)");
+        const int U = j.dbg_level[name];
+        const int C = it->second.second;
+        size_t r0, nr;
+        if (U == 0) { r0 = (size_t)j.xsegs[b].off; nr = (size_t)j.xsegs[b].len; }
+        else { r0 = (size_t)j.fsegs[b].off * U; nr = (size_t)j.fsegs[b].len * U; }
+        *data = (float*)malloc(nr * C * 4 + 4);
+        SB_CUDA(cudaSetDevice(j.v->device));
+        SB_CUDA(cudaMemcpy(*data, it->second.first + r0 * C, nr * C * 4, cudaMemcpyDeviceToHost));
+        *rows = nr; *cols = (size_t)C;
+    });
+}
+int32_t sb200_job_debug_durations(sb200_job* job, size_t b, int32_t** cum, size_t* n, sb200_error* err) {
+    return guarded(err, [&] {
+        Job& j = *job->j;
+        if (!j.ran) throw Error(19, "job not run");
+        const size_t len = (size_t)j.xsegs[b].len;
+        *cum = (int32_t*)malloc(len * 4 + 4);
+        SB_CUDA(cudaSetDevice(j.v->device));
+        SB_CUDA(cudaMemcpy(*cum, j.d_cum + j.xsegs[b].off, len * 4, cudaMemcpyDeviceToHost));
+        *n = len;
+    });
+}
+int32_t sb200_job_profile(const sb200_job* job, sb200_region_stat* out, int32_t cap) {
+    const Job& j = *job->j;
+    int32_t n = 0;
+    for (const Region& r : j.regions) {
+        if (n >= cap) break;
+        memset(&out[n], 0, sizeof(out[n]));
+        strncpy(out[n].name, r.name.c_str(), sizeof(out[n].name) - 1);
+        out[n].ms = r.ms; out[n].flops = r.flops; out[n].bytes = r.bytes; out[n].launches = r.launches;
+        n++;
+    }
+    return n;
+}
+uint64_t sb200_launch_count(void) { return g_launch_count; }
+int32_t sb200_set_backend(sb200_voice* v, int32_t backend) { int32_t p = v->v->backend; v->v->backend = backend; return p; }
+
+}  // extern "C"

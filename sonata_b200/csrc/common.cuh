@@ -1,0 +1,90 @@
+// Shared declarations for libsonata_b200 (sm_100a only).
+//
+// Activation layout everywhere: TIME-MAJOR fp32 matrices  A[row][channel]  (channel contiguous).
+// A "row" is one time step (phoneme id at the X level, frame at the Y level, sample-group at the
+// decoder levels).  Utterances of a batch are concatenated along rows as SEGMENTS; segment b
+// occupies rows [off_b, off_b + T_b) and is followed by >= HALO all-zero gap rows, so a
+// convolution that reads across a segment edge sees the zero padding the reference's B=1
+// onnxruntime run would see (piper/src/lib.rs:433-435 runs every utterance alone).
+// Every kernel that produces an activation writes ZERO into gap rows (or leaves accumulated
+// buffers untouched there), which keeps that invariant without memsets.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SB_MAX_TAPS 16
+
+namespace sb200 {
+
+// Row validity: row q is a real time step iff  q < seg_end[q / gran] * seg_mul.
+// seg_end is indexed by "granule" (64 ids at the X level, 128 frames at the Y level; a granule
+// never straddles two segments) and holds off_b + T_b in granule-level rows; decoder levels
+// that run at U x the frame rate pass gran = 128*U, seg_mul = U.
+struct RowMap {
+    const int* seg_end;
+    int gran;
+    int seg_mul;
+    int rows;   // total rows at this level
+};
+
+__device__ __forceinline__ bool row_valid(const RowMap& m, int q) {
+    if (q < 0 || q >= m.rows) return false;
+    return q < m.seg_end[q / m.gran] * m.seg_mul;
+}
+
+enum ConvAct { ACT_NONE = 0, ACT_RELU = 1, ACT_GATE = 2 };
+
+// One implicit-GEMM convolution:  for GEMM row q, output column n
+//   acc = bias[n] + sum_t sum_c  f(x[q + tap_off[t]][c]) * w[t][c][n],   f = leaky_relu(in_slope)
+//   v   = act(acc) (+ res[orow][n]) ; v *= scale ; y[orow][n] (=|+=) v,   orow = q*orow_mul + orow_add
+struct ConvArgs {
+    const float* x; int ldx; int rows_in; int cin; float in_slope;
+    const float* w; const float* bias; int ldw; int cout;
+    int ntaps; int tap_off[SB_MAX_TAPS]; int min_off; int span;   // span = max_off - min_off
+    int rows_q; int orow_mul; int orow_add;
+    RowMap map;                                                   // validity of q
+    int act; float scale;
+    const float* res; int ldres;
+    float* y0; int ldy0; int acc0; int split;                     // columns [0, split)
+    float* y1; int ldy1; int acc1;                                // columns [split, cout)
+};
+
+void launch_conv_simt(const ConvArgs& a, cudaStream_t st);
+int conv_simt_bn_for(int cout);      // column tile the SIMT kernel will use for this cout (for weight padding)
+
+// ---- misc kernels (kernels_misc.cu) ----
+void launch_embed(const int* ids_rows, const float* emb, float scale, float* x, int rows, int H, cudaStream_t st);
+// out = (res2 ? res2 : 0) + act( LN(x + (res1 ? res1 : 0)) * gamma + beta ),  act: 0 none, 1 exact GELU
+void launch_ln(const float* x, const float* res1, const float* res2, const float* gamma, const float* beta,
+               float* out, int C, int act, RowMap map, cudaStream_t st);
+// out = GELU(LN(depthwise_conv_k(x, dilation)))   (DDSConv first half)
+void launch_dw_ln_gelu(const float* x, const float* wdw /*[k][C]*/, const float* bdw, int k, int dil,
+                       const float* gamma, const float* beta, float* out, int C, RowMap map, cudaStream_t st);
+struct SegInfo { int off; int len; };   // rows
+void launch_attention(const float* qkv, int ldq, const float* relk, const float* relv, int window,
+                      float* out, int ldo, int H, int heads, const SegInfo* segs, int nseg, int max_len,
+                      cudaStream_t st);
+size_t attention_smem_bytes(int max_len, int D);
+// h[r][c] = w[c]*z[r][zcol] + b[c] + g[r][c]
+void launch_flow_pre(const float* z, int zcol, const float* w, const float* b, const float* g, float* h,
+                     int C, RowMap map, cudaStream_t st);
+// z[r][tcol] = RQS^-1(z[r][tcol]; params h29[r][0..3*bins-1))
+void launch_spline(const float* h29, int ldh, float* z, int tcol, int bins, float inv_sqrt_filter,
+                   RowMap map, cudaStream_t st);
+// logw = (z[:,0]-m0)*exp(-logs0); w = exp(logw)*length_scale; w_ceil; per-segment inclusive scan
+void launch_durations(const float* z, float m0, float logs0, float length_scale, const SegInfo* segs, int nseg,
+                      float* logw, int* cum, int* y_len, cudaStream_t st);
+struct FrameSeg { int off; int len; int xoff; int xlen; long long out_off; };
+// z_p rows: gather m_p/logs_p of the token whose cumulative duration covers the frame, add noise
+void launch_expand(const float* stats, int ldst, int I, const int* cum, const float* eps, float noise_scale,
+                   float* zp, const FrameSeg* fsegs, const int* ftile_seg, RowMap ymap, cudaStream_t st);
+// wav = tanh(conv_k7(lrelu_{0.01}(x)))  ->  compact per-segment output
+void launch_conv_post(const float* x, int C, const float* w /*[7][C]*/, float* wav, const FrameSeg* fsegs,
+                      const int* ftile_seg, int U, RowMap map, cudaStream_t st);
+void launch_randn(float* out, long long n, unsigned long long seed, unsigned long long stream_id, cudaStream_t st);
+void launch_scale_copy2(const float* eps, float s, float* z, RowMap map, cudaStream_t st);   // z[r][0..1] = eps*s
+void launch_fill_zero(float* p, long long n, cudaStream_t st);
+
+extern unsigned long long g_launch_count;   // kernels launched by this library (host-side counter)
+
+}  // namespace sb200

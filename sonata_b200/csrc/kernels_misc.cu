@@ -1,0 +1,632 @@
+// Non-GEMM stages of the Piper/VITS path as sm_100a kernels: embedding, channel LayerNorm
+// (warp-shuffle reductions), DDSConv depthwise stage, relative-position attention, the
+// duration-predictor spline flow, the duration ceil/scan, the monotonic-alignment expansion
+// (generate_path restated as a gather), conv_post+tanh and the Philox noise source.
+// The reference executes all of these inside onnxruntime (piper/src/lib.rs:362-379); the
+// arithmetic restated here follows oracle/vits_oracle.py function by function.
+#include "common.cuh"
+#include <math.h>
+
+namespace sb200 {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
+// ------------------------------------------------------------------ embedding
+// oracle: text_encoder()  x = emb[ids] * sqrt(H)
+__global__ void embed_kernel(const int* __restrict__ ids, const float* __restrict__ emb, float scale,
+                             float* __restrict__ x, int rows, int H) {
+    const int h4 = H / 4;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)rows * h4) return;
+    const int r = (int)(i / h4), c = (int)(i % h4);
+    const int id = ids[r];
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (id >= 0) {
+        v = reinterpret_cast<const float4*>(emb + (size_t)id * H)[c];
+        v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    }
+    reinterpret_cast<float4*>(x + (size_t)r * H)[c] = v;
+}
+
+// ------------------------------------------------------------------ channel LayerNorm (one warp per row)
+// oracle: _layer_norm()  (eps = 1e-5, biased variance, two-pass)
+template <int NV>
+__global__ void __launch_bounds__(256) ln_kernel(const float* __restrict__ x, const float* __restrict__ res1,
+                                                 const float* __restrict__ res2, const float* __restrict__ gamma,
+                                                 const float* __restrict__ beta, float* __restrict__ out, int act,
+                                                 RowMap map) {
+    constexpr int C = NV * 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 8 + warp;
+    if (r >= map.rows) return;
+    float* o = out + (size_t)r * C;
+    if (!row_valid(map, r)) {
+#pragma unroll
+        for (int j = 0; j < NV; j++) o[lane + 32 * j] = 0.f;
+        return;
+    }
+    float v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+        float t = x[(size_t)r * C + lane + 32 * j];
+        if (res1) t += res1[(size_t)r * C + lane + 32 * j];
+        v[j] = t;
+        s += t;
+    }
+    const float mean = warp_sum(s) * (1.f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; j++) { const float d = v[j] - mean; q += d * d; }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + 1e-5f);
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+        const int c = lane + 32 * j;
+        float y = (v[j] - mean) * rstd * gamma[c] + beta[c];
+        if (act == 1) y = gelu_exact(y);
+        if (res2) y += res2[(size_t)r * C + c];
+        o[c] = y;
+    }
+}
+
+// ------------------------------------------------------------------ DDSConv: depthwise conv + LN + GELU
+// oracle: _dds()  y = gelu(LN(conv_sep(x)))
+template <int NV>
+__global__ void __launch_bounds__(256) dw_ln_gelu_kernel(const float* __restrict__ x, const float* __restrict__ wdw,
+                                                         const float* __restrict__ bdw, int k, int dil,
+                                                         const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, float* __restrict__ out,
+                                                         RowMap map) {
+    constexpr int C = NV * 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 8 + warp;
+    if (r >= map.rows) return;
+    float* o = out + (size_t)r * C;
+    if (!row_valid(map, r)) {
+#pragma unroll
+        for (int j = 0; j < NV; j++) o[lane + 32 * j] = 0.f;
+        return;
+    }
+    float v[NV];
+#pragma unroll
+    for (int j = 0; j < NV; j++) v[j] = bdw[lane + 32 * j];
+    const int half = (k - 1) / 2;
+    for (int t = 0; t < k; t++) {
+        const int rr = r + (t - half) * dil;
+        if (rr < 0 || rr >= map.rows) continue;   // gap rows hold zeros, so no per-segment test needed
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            const int c = lane + 32 * j;
+            v[j] = fmaf(wdw[t * C + c], x[(size_t)rr * C + c], v[j]);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; j++) s += v[j];
+    const float mean = warp_sum(s) * (1.f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; j++) { const float d = v[j] - mean; q += d * d; }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + 1e-5f);
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+        const int c = lane + 32 * j;
+        o[c] = gelu_exact((v[j] - mean) * rstd * gamma[c] + beta[c]);
+    }
+}
+
+// ------------------------------------------------------------------ relative-position attention
+// oracle: _mha()   one CTA = (16 query rows, head, segment); 2*D threads.
+//   scores[i][j] = (q_i/sqrt(D)).k_j + [|j-i|<=w] (q_i/sqrt(D)).E_k[j-i+w]
+//   out_i = softmax(scores_i) . V + sum_{|d|<=w} p[i][i+d] E_v[d+w]
+constexpr int ATT_QT = 16;
+
+template <int D>
+__global__ void __launch_bounds__(2 * D) attention_kernel(const float* __restrict__ qkv, int ldq,
+                                                          const float* __restrict__ relk,
+                                                          const float* __restrict__ relv, int window,
+                                                          float* __restrict__ out, int ldo, int H,
+                                                          const SegInfo* __restrict__ segs, int tpad) {
+    const SegInfo sg = segs[blockIdx.z];
+    const int T = sg.len;
+    const int i0 = blockIdx.x * ATT_QT;
+    if (i0 >= T) return;
+    const int head = blockIdx.y;
+    const int tid = threadIdx.x;
+    constexpr int NT = 2 * D;
+    const int nrel = 2 * window + 1;
+
+    extern __shared__ __align__(16) float sm[];
+    float* Qs = sm;                               // [QT][D]
+    float* S = Qs + ATT_QT * D;                   // [QT][tpad]
+    float* qE = S + ATT_QT * tpad;                // [QT][nrel]
+    float* inv = qE + ATT_QT * nrel;              // [QT]
+    float* Osum = inv + ATT_QT;                   // [2][QT][D] partial outputs of the two j-halves
+
+    const float* qbase = qkv + (size_t)sg.off * ldq + head * D;
+    const float* kbase = qbase + H;
+    const float* vbase = qbase + 2 * H;
+    const float qscale = rsqrtf((float)D);
+
+    for (int idx = tid; idx < ATT_QT * D; idx += NT) {
+        const int i = idx / D, c = idx % D;
+        Qs[idx] = (i0 + i < T) ? qbase[(size_t)(i0 + i) * ldq + c] * qscale : 0.f;
+    }
+    __syncthreads();
+    // relative-key logits
+    for (int idx = tid; idx < ATT_QT * nrel; idx += NT) {
+        const int i = idx / nrel, d = idx % nrel;
+        float s = 0.f;
+        for (int c = 0; c < D; c++) s = fmaf(Qs[i * D + c], relk[d * D + c], s);
+        qE[idx] = s;
+    }
+    // scores: one key per thread per pass
+    for (int j = tid; j < T; j += NT) {
+        float acc[ATT_QT];
+#pragma unroll
+        for (int i = 0; i < ATT_QT; i++) acc[i] = 0.f;
+        const float4* kr = reinterpret_cast<const float4*>(kbase + (size_t)j * ldq);
+#pragma unroll 2
+        for (int c4 = 0; c4 < D / 4; c4++) {
+            const float4 kv = kr[c4];
+#pragma unroll
+            for (int i = 0; i < ATT_QT; i++) {
+                const float4 qv = *reinterpret_cast<const float4*>(Qs + i * D + c4 * 4);
+                acc[i] = fmaf(qv.x, kv.x, acc[i]);
+                acc[i] = fmaf(qv.y, kv.y, acc[i]);
+                acc[i] = fmaf(qv.z, kv.z, acc[i]);
+                acc[i] = fmaf(qv.w, kv.w, acc[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < ATT_QT; i++) S[i * tpad + j] = acc[i];
+    }
+    __syncthreads();
+    // add relative logits, softmax (one warp per query row, round-robin)
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int i = warp; i < ATT_QT; i += NT / 32) {
+        const int ia = i0 + i;
+        if (ia >= T) { if (lane == 0) inv[i] = 0.f; continue; }
+        float* Sr = S + i * tpad;
+        if (lane < nrel) {
+            const int j = ia + lane - window;
+            if (j >= 0 && j < T) Sr[j] += qE[i * nrel + lane];
+        }
+        __syncwarp();
+        float m = -INFINITY;
+        for (int j = lane; j < T; j += 32) m = fmaxf(m, Sr[j]);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int j = lane; j < T; j += 32) { const float e = expf(Sr[j] - m); Sr[j] = e; s += e; }
+        s = warp_sum(s);
+        if (lane == 0) inv[i] = 1.f / s;
+    }
+    // zero the tail so the float4 loop below may over-read up to tpad
+    for (int idx = tid; idx < ATT_QT * (tpad - T); idx += NT) {
+        const int i = idx / (tpad - T), j = T + idx % (tpad - T);
+        S[i * tpad + j] = 0.f;
+    }
+    __syncthreads();
+    // P.V : thread = (half, channel)
+    {
+        const int half = tid / D, c = tid % D;
+        float acc[ATT_QT];
+#pragma unroll
+        for (int i = 0; i < ATT_QT; i++) acc[i] = 0.f;
+        const int nj4 = tpad / 4;
+        for (int j4 = half; j4 < nj4; j4 += 2) {
+            float vv[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int j = j4 * 4 + e;
+                vv[e] = j < T ? vbase[(size_t)j * ldq + c] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < ATT_QT; i++) {
+                const float4 p = *reinterpret_cast<const float4*>(S + i * tpad + j4 * 4);
+                acc[i] = fmaf(p.x, vv[0], acc[i]);
+                acc[i] = fmaf(p.y, vv[1], acc[i]);
+                acc[i] = fmaf(p.z, vv[2], acc[i]);
+                acc[i] = fmaf(p.w, vv[3], acc[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < ATT_QT; i++) Osum[(half * ATT_QT + i) * D + c] = acc[i];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < ATT_QT * D; idx += NT) {
+        const int i = idx / D, c = idx % D;
+        const int ia = i0 + i;
+        if (ia >= T) continue;
+        float o = Osum[i * D + c] + Osum[(ATT_QT + i) * D + c];
+        for (int d = 0; d < nrel; d++) {
+            const int j = ia + d - window;
+            if (j >= 0 && j < T) o = fmaf(S[i * tpad + j], relv[d * D + c], o);
+        }
+        out[(size_t)(sg.off + ia) * ldo + head * D + c] = o * inv[i];
+    }
+}
+
+// ------------------------------------------------------------------ duration-predictor flow pieces
+// oracle: _conv_flow_reverse()  h = pre(z0) + g
+__global__ void flow_pre_kernel(const float* __restrict__ z, int zcol, const float* __restrict__ w,
+                                const float* __restrict__ b, const float* __restrict__ g, float* __restrict__ h,
+                                int C, RowMap map) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)map.rows * C) return;
+    const int r = (int)(i / C), c = (int)(i % C);
+    h[i] = row_valid(map, r) ? fmaf(w[c], z[2 * r + zcol], b[c]) + g[i] : 0.f;
+}
+
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+
+// oracle: _rqs_inverse()  (tails = linear, bound 5, min bin w/h 1e-3, min derivative 1e-3)
+template <int NB>
+__global__ void spline_kernel(const float* __restrict__ h29, int ldh, float* __restrict__ z, int tcol,
+                              float inv_sqrt_filter, RowMap map) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= map.rows) return;
+    if (!row_valid(map, r)) { z[2 * r + tcol] = 0.f; return; }
+    const float x = z[2 * r + tcol];
+    const float B = 5.0f;
+    if (!(x >= -B && x <= B)) return;   // identity outside the tails
+    const float* h = h29 + (size_t)r * ldh;
+    float cw[NB + 1], ch[NB + 1], dv[NB + 1];
+    // widths
+    {
+        float u[NB], m = -INFINITY, s = 0.f;
+#pragma unroll
+        for (int k = 0; k < NB; k++) { u[k] = h[k] * inv_sqrt_filter; m = fmaxf(m, u[k]); }
+#pragma unroll
+        for (int k = 0; k < NB; k++) { u[k] = expf(u[k] - m); s += u[k]; }
+        float c = 0.f;
+        cw[0] = -B;
+#pragma unroll
+        for (int k = 0; k < NB; k++) {
+            const float wk = 1e-3f + (1.f - 1e-3f * NB) * (u[k] / s);
+            c += wk;
+            cw[k + 1] = 2.f * B * c + (-B);
+        }
+        cw[NB] = B;
+    }
+    {
+        float u[NB], m = -INFINITY, s = 0.f;
+#pragma unroll
+        for (int k = 0; k < NB; k++) { u[k] = h[NB + k] * inv_sqrt_filter; m = fmaxf(m, u[k]); }
+#pragma unroll
+        for (int k = 0; k < NB; k++) { u[k] = expf(u[k] - m); s += u[k]; }
+        float c = 0.f;
+        ch[0] = -B;
+#pragma unroll
+        for (int k = 0; k < NB; k++) {
+            const float hk = 1e-3f + (1.f - 1e-3f * NB) * (u[k] / s);
+            c += hk;
+            ch[k + 1] = 2.f * B * c + (-B);
+        }
+        ch[NB] = B;
+    }
+    {
+        const float cst = logf(expf(1.f - 1e-3f) - 1.f);
+        dv[0] = 1e-3f + softplus_f(cst);
+        dv[NB] = dv[0];
+#pragma unroll
+        for (int k = 1; k < NB; k++) dv[k] = 1e-3f + softplus_f(h[2 * NB + k - 1]);
+    }
+    int bin = -1;
+#pragma unroll
+    for (int k = 0; k <= NB; k++) {
+        const float loc = (k == NB) ? ch[k] + 1e-6f : ch[k];
+        bin += (x >= loc) ? 1 : 0;
+    }
+    bin = min(max(bin, 0), NB - 1);
+    float in_cw = 0, in_w = 0, in_ch = 0, in_h = 0, in_d = 0, in_d1 = 0;
+#pragma unroll
+    for (int k = 0; k < NB; k++)
+        if (k == bin) {
+            in_cw = cw[k]; in_w = cw[k + 1] - cw[k];
+            in_ch = ch[k]; in_h = ch[k + 1] - ch[k];
+            in_d = dv[k]; in_d1 = dv[k + 1];
+        }
+    const float delta = in_h / in_w;
+    const float t = x - in_ch;
+    const float e = in_d + in_d1 - 2.f * delta;
+    const float a = t * e + in_h * (delta - in_d);
+    const float b = in_h * in_d - t * e;
+    const float c = -delta * t;
+    const float disc = b * b - 4.f * a * c;
+    const float root = (2.f * c) / (-b - sqrtf(disc));
+    z[2 * r + tcol] = root * in_w + in_cw;
+}
+
+// z[r][0..1] = eps[r][0..1] * s   (oracle: sdp_reverse  z = eps_w * noise_w)
+__global__ void scale_copy2_kernel(const float* __restrict__ eps, float s, float* __restrict__ z, RowMap map) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= map.rows) return;
+    const bool v = row_valid(map, r) && eps != nullptr;
+    z[2 * r] = v ? eps[2 * r] * s : 0.f;
+    z[2 * r + 1] = v ? eps[2 * r + 1] * s : 0.f;
+}
+
+// ------------------------------------------------------------------ durations: ceil + inclusive scan
+// oracle: sdp_reverse() tail (ElementwiseAffine^-1) + durations()
+__global__ void __launch_bounds__(256) durations_kernel(const float* __restrict__ z, float m0, float logs0,
+                                                        float length_scale, const SegInfo* __restrict__ segs,
+                                                        float* __restrict__ logw, int* __restrict__ cum,
+                                                        int* __restrict__ y_len) {
+    const SegInfo sg = segs[blockIdx.x];
+    __shared__ int warp_tot[8];
+    __shared__ int carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    const float einv = expf(-logs0);
+    for (int base = 0; base < sg.len; base += 256) {
+        const int i = base + tid;
+        int w = 0;
+        if (i < sg.len) {
+            const float lw = (z[2 * (sg.off + i)] - m0) * einv;
+            logw[sg.off + i] = lw;
+            w = (int)ceilf(expf(lw) * length_scale);
+        }
+        int s = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += t;
+        }
+        if (lane == 31) warp_tot[warp] = s;
+        __syncthreads();
+        int pre = carry_s;
+        for (int k = 0; k < warp; k++) pre += warp_tot[k];
+        if (i < sg.len) cum[sg.off + i] = pre + s;
+        __syncthreads();
+        if (tid == 255) carry_s = pre + s;
+        __syncthreads();
+    }
+    if (tid == 0) y_len[blockIdx.x] = max(carry_s, 1);
+}
+
+// ------------------------------------------------------------------ alignment expansion (one warp per frame)
+// oracle: expand()   frame j takes token i iff cum[i-1] <= j < cum[i]
+__global__ void __launch_bounds__(256) expand_kernel(const float* __restrict__ stats, int ldst, int I,
+                                                     const int* __restrict__ cum, const float* __restrict__ eps,
+                                                     float noise_scale, float* __restrict__ zp,
+                                                     const FrameSeg* __restrict__ fsegs,
+                                                     const int* __restrict__ ftile_seg, RowMap ymap) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 8 + warp;
+    if (r >= ymap.rows) return;
+    float* o = zp + (size_t)r * I;
+    if (!row_valid(ymap, r)) {
+        for (int c = lane; c < I; c += 32) o[c] = 0.f;
+        return;
+    }
+    const FrameSeg fs = fsegs[ftile_seg[r / ymap.gran]];
+    const int j = r - fs.off;
+    const int* cm = cum + fs.xoff;
+    int lo = 0, hi = fs.xlen;          // first i with cm[i] > j
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (cm[mid] > j) hi = mid; else lo = mid + 1;
+    }
+    if (lo >= fs.xlen) {               // only when sum(w_ceil) == 0 and y_len was clamped to 1
+        for (int c = lane; c < I; c += 32) o[c] = (eps && noise_scale != 0.f) ? eps[(size_t)r * I + c] * noise_scale : 0.f;
+        return;
+    }
+    const float* st = stats + (size_t)(fs.xoff + lo) * ldst;
+    for (int c = lane; c < I; c += 32) {
+        float v = st[c];
+        if (eps && noise_scale != 0.f) v += eps[(size_t)r * I + c] * expf(st[I + c]) * noise_scale;
+        o[c] = v;
+    }
+}
+
+// ------------------------------------------------------------------ conv_post + tanh (C -> 1, k = 7)
+// oracle: decoder() tail.  One thread per output sample; a CTA stages its rows (+3 halo) in smem.
+template <int C>
+__global__ void __launch_bounds__(256) conv_post_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        float* __restrict__ wav, const FrameSeg* __restrict__ fsegs,
+                                                        const int* __restrict__ ftile_seg, int U, RowMap map) {
+    constexpr int ROWS = 256, HALO = 3, ST = C + 1;
+    extern __shared__ float sm[];
+    float* xs = sm;                       // [(ROWS+2*HALO)][C+1], leaky-relu(0.01) applied
+    float* ws = xs + (ROWS + 2 * HALO) * ST;   // [7][C]
+    const int r0 = blockIdx.x * ROWS;
+    for (int i = threadIdx.x; i < 7 * C; i += 256) ws[i] = w[i];
+    for (int i = threadIdx.x; i < (ROWS + 2 * HALO) * (C / 4); i += 256) {
+        const int rr = i / (C / 4), c4 = i % (C / 4);
+        const int gr = r0 - HALO + rr;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gr >= 0 && gr < map.rows) v = reinterpret_cast<const float4*>(x + (size_t)gr * C)[c4];
+        float* d = xs + rr * ST + c4 * 4;
+        d[0] = v.x > 0.f ? v.x : 0.01f * v.x;
+        d[1] = v.y > 0.f ? v.y : 0.01f * v.y;
+        d[2] = v.z > 0.f ? v.z : 0.01f * v.z;
+        d[3] = v.w > 0.f ? v.w : 0.01f * v.w;
+    }
+    __syncthreads();
+    const int r = r0 + threadIdx.x;
+    if (r >= map.rows || !row_valid(map, r)) return;
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 7; t++) {
+        const float* xr = xs + (threadIdx.x + t) * ST;
+#pragma unroll 8
+        for (int c = 0; c < C; c++) acc = fmaf(xr[c], ws[t * C + c], acc);
+    }
+    const FrameSeg fs = fsegs[ftile_seg[r / map.gran]];
+    wav[fs.out_off + (long long)(r - (long long)fs.off * U)] = tanhf(acc);
+}
+
+// ------------------------------------------------------------------ Philox4x32-10 -> N(0,1)
+__device__ __forceinline__ void philox_round(unsigned& c0, unsigned& c1, unsigned& c2, unsigned& c3, unsigned k0,
+                                             unsigned k1) {
+    const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
+    const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+    const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0;
+    const unsigned n1 = (unsigned)p1;
+    const unsigned n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1;
+    const unsigned n3 = (unsigned)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+}
+
+__global__ void randn_kernel(float* __restrict__ out, long long n, unsigned long long seed,
+                             unsigned long long stream_id) {
+    const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i4 * 4 >= n) return;
+    unsigned c0 = (unsigned)i4, c1 = (unsigned)(i4 >> 32), c2 = (unsigned)stream_id, c3 = (unsigned)(stream_id >> 32);
+    unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        philox_round(c0, c1, c2, c3, k0, k1);
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    const float u0 = ((float)c0 + 0.5f) * 2.3283064365386963e-10f;
+    const float u1 = ((float)c1 + 0.5f) * 2.3283064365386963e-10f;
+    const float u2 = ((float)c2 + 0.5f) * 2.3283064365386963e-10f;
+    const float u3 = ((float)c3 + 0.5f) * 2.3283064365386963e-10f;
+    const float r0 = sqrtf(-2.f * logf(u0)), r1 = sqrtf(-2.f * logf(u2));
+    float s0, cs0, s1, cs1;
+    sincosf(6.283185307179586f * u1, &s0, &cs0);
+    sincosf(6.283185307179586f * u3, &s1, &cs1);
+    const float v[4] = {r0 * cs0, r0 * s0, r1 * cs1, r1 * s1};
+    for (int e = 0; e < 4; e++)
+        if (i4 * 4 + e < n) out[i4 * 4 + e] = v[e];
+}
+
+__global__ void fill_zero_kernel(float4* p, long long n4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n4) p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+template <typename K>
+void set_smem(K kern, size_t bytes) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+}  // namespace
+
+// ====================================================================== launchers
+void launch_embed(const int* ids_rows, const float* emb, float scale, float* x, int rows, int H, cudaStream_t st) {
+    const long long n = (long long)rows * (H / 4);
+    embed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ids_rows, emb, scale, x, rows, H);
+    g_launch_count++;
+}
+
+void launch_ln(const float* x, const float* res1, const float* res2, const float* gamma, const float* beta,
+               float* out, int C, int act, RowMap map, cudaStream_t st) {
+    const unsigned grid = (map.rows + 7) / 8;
+    switch (C) {
+        case 96: ln_kernel<3><<<grid, 256, 0, st>>>(x, res1, res2, gamma, beta, out, act, map); break;
+        case 192: ln_kernel<6><<<grid, 256, 0, st>>>(x, res1, res2, gamma, beta, out, act, map); break;
+        case 256: ln_kernel<8><<<grid, 256, 0, st>>>(x, res1, res2, gamma, beta, out, act, map); break;
+        default: break;
+    }
+    g_launch_count++;
+}
+
+void launch_dw_ln_gelu(const float* x, const float* wdw, const float* bdw, int k, int dil, const float* gamma,
+                       const float* beta, float* out, int C, RowMap map, cudaStream_t st) {
+    const unsigned grid = (map.rows + 7) / 8;
+    switch (C) {
+        case 96: dw_ln_gelu_kernel<3><<<grid, 256, 0, st>>>(x, wdw, bdw, k, dil, gamma, beta, out, map); break;
+        case 192: dw_ln_gelu_kernel<6><<<grid, 256, 0, st>>>(x, wdw, bdw, k, dil, gamma, beta, out, map); break;
+        case 256: dw_ln_gelu_kernel<8><<<grid, 256, 0, st>>>(x, wdw, bdw, k, dil, gamma, beta, out, map); break;
+        default: break;
+    }
+    g_launch_count++;
+}
+
+static int att_tpad(int max_len) { return (max_len + 3) & ~3; }
+
+size_t attention_smem_bytes(int max_len, int D) {
+    const int tpad = att_tpad(max_len);
+    return sizeof(float) * ((size_t)ATT_QT * D + (size_t)ATT_QT * tpad + ATT_QT * 32 + ATT_QT + 2 * ATT_QT * D);
+}
+
+void launch_attention(const float* qkv, int ldq, const float* relk, const float* relv, int window, float* out,
+                      int ldo, int H, int heads, const SegInfo* segs, int nseg, int max_len, cudaStream_t st) {
+    const int D = H / heads;
+    const int tpad = att_tpad(max_len);
+    const size_t smem = attention_smem_bytes(max_len, D);
+    dim3 grid((max_len + ATT_QT - 1) / ATT_QT, heads, nseg);
+    if (D == 96) {
+        set_smem(attention_kernel<96>, smem);
+        attention_kernel<96><<<grid, 192, smem, st>>>(qkv, ldq, relk, relv, window, out, ldo, H, segs, tpad);
+    } else if (D == 48) {
+        set_smem(attention_kernel<48>, smem);
+        attention_kernel<48><<<grid, 96, smem, st>>>(qkv, ldq, relk, relv, window, out, ldo, H, segs, tpad);
+    }
+    g_launch_count++;
+}
+
+void launch_flow_pre(const float* z, int zcol, const float* w, const float* b, const float* g, float* h, int C,
+                     RowMap map, cudaStream_t st) {
+    const long long n = (long long)map.rows * C;
+    flow_pre_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(z, zcol, w, b, g, h, C, map);
+    g_launch_count++;
+}
+
+void launch_spline(const float* h29, int ldh, float* z, int tcol, int bins, float inv_sqrt_filter, RowMap map,
+                   cudaStream_t st) {
+    (void)bins;   // 10 bins is the only configuration Piper ships
+    spline_kernel<10><<<(map.rows + 127) / 128, 128, 0, st>>>(h29, ldh, z, tcol, inv_sqrt_filter, map);
+    g_launch_count++;
+}
+
+void launch_scale_copy2(const float* eps, float s, float* z, RowMap map, cudaStream_t st) {
+    scale_copy2_kernel<<<(map.rows + 255) / 256, 256, 0, st>>>(eps, s, z, map);
+    g_launch_count++;
+}
+
+void launch_durations(const float* z, float m0, float logs0, float length_scale, const SegInfo* segs, int nseg,
+                      float* logw, int* cum, int* y_len, cudaStream_t st) {
+    durations_kernel<<<nseg, 256, 0, st>>>(z, m0, logs0, length_scale, segs, logw, cum, y_len);
+    g_launch_count++;
+}
+
+void launch_expand(const float* stats, int ldst, int I, const int* cum, const float* eps, float noise_scale,
+                   float* zp, const FrameSeg* fsegs, const int* ftile_seg, RowMap ymap, cudaStream_t st) {
+    expand_kernel<<<(ymap.rows + 7) / 8, 256, 0, st>>>(stats, ldst, I, cum, eps, noise_scale, zp, fsegs, ftile_seg,
+                                                       ymap);
+    g_launch_count++;
+}
+
+void launch_conv_post(const float* x, int C, const float* w, float* wav, const FrameSeg* fsegs,
+                      const int* ftile_seg, int U, RowMap map, cudaStream_t st) {
+    const unsigned grid = (map.rows + 255) / 256;
+    const size_t smem = sizeof(float) * ((size_t)(256 + 6) * (C + 1) + 7 * C);
+    switch (C) {
+        case 16: set_smem(conv_post_kernel<16>, smem); conv_post_kernel<16><<<grid, 256, smem, st>>>(x, w, wav, fsegs, ftile_seg, U, map); break;
+        case 32: set_smem(conv_post_kernel<32>, smem); conv_post_kernel<32><<<grid, 256, smem, st>>>(x, w, wav, fsegs, ftile_seg, U, map); break;
+        case 64: set_smem(conv_post_kernel<64>, smem); conv_post_kernel<64><<<grid, 256, smem, st>>>(x, w, wav, fsegs, ftile_seg, U, map); break;
+        default: break;
+    }
+    g_launch_count++;
+}
+
+void launch_randn(float* out, long long n, unsigned long long seed, unsigned long long stream_id, cudaStream_t st) {
+    const long long n4 = (n + 3) / 4;
+    randn_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(out, n, seed, stream_id);
+    g_launch_count++;
+}
+
+void launch_fill_zero(float* p, long long n, cudaStream_t st) {
+    const long long n4 = n / 4;
+    fill_zero_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<float4*>(p), n4);
+    g_launch_count++;
+}
+
+}  // namespace sb200
