@@ -71,7 +71,8 @@ int32_t sb200_device_count(void);
 
 /* ---- voice: sonata_piper::from_config_path (piper/src/lib.rs:88-110) ----
  * `config_path` is the Piper `<voice>.onnx.json`; weights are read from the sibling `<voice>.svw`
- * (where the reference opens `<voice>.onnx`).  `device` = CUDA ordinal. */
+ * (where the reference opens `<voice>.onnx`).  `device` = CUDA ordinal; -1 loads the config only
+ * (host-side queries and id mapping work, every synthesis call fails with OPERATION_ERROR). */
 int32_t sb200_voice_load(const char* config_path, int32_t device, sb200_voice** out, sb200_error* err);
 void sb200_voice_free(sb200_voice* v);
 

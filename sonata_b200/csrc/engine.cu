@@ -78,6 +78,8 @@ Job::~Job() {
 Job* create_job(Voice* v, const long long* ids, const size_t* offs, size_t B, const float* const* eps_w,
                 const float* const* eps_z, const size_t* eps_z_frames, bool debug) {
     if (B == 0) throw Error(19, "empty batch");
+    if (v->device < 0 || !v->emb)
+        throw Error(19, "Failed to run model inference. Error: voice was loaded config-only (device -1); libsonata_b200 has no CPU path");
     std::unique_ptr<Job> j(new Job());
     j->v = v; j->B = B; j->debug = debug;
     {

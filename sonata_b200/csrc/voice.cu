@@ -191,6 +191,7 @@ std::vector<long long> Voice::phonemes_to_ids(const char* utf8) const {
 }
 
 Voice::~Voice() {
+    if (device < 0) return;
     cudaSetDevice(device);
     for (Context* c : pool) delete c;
     for (void* p : dev_allocs) cudaFree(p);
@@ -234,6 +235,8 @@ Voice* load_voice(const std::string& config_path, int device) {
         if (kv.second->kind != sbjson::Value::Arr || kv.second->arr.empty()) continue;
         v->phoneme_first_id[first_code_point(kv.first)] = (long long)kv.second->arr[0]->num;
     }
+
+    if (device == -1) return v.release();   // config-only handle (host logic, id mapping): no synthesis possible
 
     // weights: `<name>.onnx.json` -> `<name>.svw` (the reference opens `<name>.onnx`, :98-108)
     std::string stem = config_path;

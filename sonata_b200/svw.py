@@ -34,7 +34,7 @@ def write_svw(path, tensors: "OrderedDict[str, np.ndarray]") -> None:
         f.write(MAGIC)
         f.write(struct.pack("<I", len(tensors)))
         for name, arr in tensors.items():
-            arr = np.ascontiguousarray(arr)
+            arr = np.asarray(arr, order="C")
             if arr.dtype == np.float32:
                 dt = 0
             elif arr.dtype == np.int32:
