@@ -159,6 +159,13 @@ typedef struct sb200_region_stat {
 } sb200_region_stat;
 /* region statistics of the last run of `job`; returns the number written (<= cap) */
 int32_t sb200_job_profile(const sb200_job* job, sb200_region_stat* out, int32_t cap);
+/* one convolution on caller data through either backend (kernel unit tests):
+ * y[rows][cout] (=|+=) scale * (act(bias + conv_k,dil(lrelu_slope(x))) + res); w is [cout][cin][k];
+ * act 0 none, 1 relu, 2 tanh*sigmoid gate (y is [rows][cout/2]); rows >= valid_rows are masked. */
+int32_t sb200_debug_conv(int32_t device, int32_t backend, const float* x, int32_t rows, int32_t cin, const float* w,
+                         const float* bias, int32_t cout, int32_t k, int32_t dil, float in_slope, int32_t act,
+                         const float* res, float scale, int32_t accumulate, float* y, int32_t valid_rows,
+                         sb200_error* err);
 /* kernels launched by this library since load (host-side counter) */
 uint64_t sb200_launch_count(void);
 /* select the contraction backend: 0 = fp32 CUDA-core implicit GEMM, 1 = tcgen05 (3xTF32) where

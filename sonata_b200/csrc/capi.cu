@@ -296,6 +296,43 @@ int32_t sb200_job_profile(const sb200_job* job, sb200_region_stat* out, int32_t 
     }
     return n;
 }
+int32_t sb200_debug_conv(int32_t device, int32_t backend, const float* x, int32_t rows, int32_t cin, const float* w,
+                         const float* bias, int32_t cout, int32_t k, int32_t dil, float in_slope, int32_t act,
+                         const float* res, float scale, int32_t accumulate, float* y, int32_t valid_rows,
+                         sb200_error* err) {
+    return guarded(err, [&] {
+        SB_CUDA(cudaSetDevice(device));
+        Voice tmp; tmp.device = device;
+        ConvW cw = debug_make_conv(tmp, w, bias, cout, cin, k, dil);
+        const int R = (rows + 255) / 256 * 256;
+        const int ycols = act == ACT_GATE ? cout / 2 : cout;
+        float *dx, *dy, *dres = nullptr; int* dend;
+        SB_CUDA(cudaMalloc(&dx, (size_t)R * cin * 4)); SB_CUDA(cudaMemset(dx, 0, (size_t)R * cin * 4));
+        SB_CUDA(cudaMemcpy(dx, x, (size_t)rows * cin * 4, cudaMemcpyHostToDevice));
+        SB_CUDA(cudaMalloc(&dy, (size_t)R * ycols * 4)); SB_CUDA(cudaMemset(dy, 0, (size_t)R * ycols * 4));
+        SB_CUDA(cudaMemcpy(dy, y, (size_t)rows * ycols * 4, cudaMemcpyHostToDevice));
+        if (res) { SB_CUDA(cudaMalloc(&dres, (size_t)R * cout * 4)); SB_CUDA(cudaMemset(dres, 0, (size_t)R * cout * 4));
+                   SB_CUDA(cudaMemcpy(dres, res, (size_t)rows * cout * 4, cudaMemcpyHostToDevice)); }
+        SB_CUDA(cudaMalloc(&dend, 4)); SB_CUDA(cudaMemcpy(dend, &valid_rows, 4, cudaMemcpyHostToDevice));
+        ConvArgs p{};
+        p.x = dx; p.ldx = cin; p.rows_in = R; p.cin = cin; p.in_slope = in_slope;
+        p.w = cw.w; p.bias = cw.bias; p.ldw = cw.ldw; p.cout = cw.cout; p.wtc = cw.wtc; p.tc_nt = cw.tc_nt;
+        p.ntaps = cw.ntaps; memcpy(p.tap_off, cw.tap_off, sizeof(p.tap_off)); p.min_off = cw.min_off; p.span = cw.span;
+        p.rows_q = R; p.orow_mul = 1; p.orow_add = 0;
+        p.map = RowMap{dend, R, 1, R};
+        p.act = act; p.scale = scale; p.res = dres; p.ldres = cout;
+        p.y0 = dy; p.ldy0 = ycols; p.acc0 = accumulate; p.split = cout; p.y1 = dy; p.ldy1 = ycols; p.acc1 = accumulate;
+        if (backend == 1) {
+            if (!conv_tc_supported(p)) throw Error(19, "conv shape not supported by the tcgen05 backend");
+            launch_conv_tc(p, 0);
+        } else launch_conv_simt(p, 0);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) e = cudaMemcpy(y, dy, (size_t)rows * ycols * 4, cudaMemcpyDeviceToHost);
+        cudaFree(dx); cudaFree(dy); cudaFree(dend); if (dres) cudaFree(dres);
+        if (e != cudaSuccess) throw Error(19, std::string("CUDA error: ") + cudaGetErrorString(e));
+    });
+}
+
 uint64_t sb200_launch_count(void) { return g_launch_count; }
 int32_t sb200_set_backend(sb200_voice* v, int32_t backend) { int32_t p = v->v->backend; v->v->backend = backend; return p; }
 

@@ -10,8 +10,6 @@
 
 namespace sb200 {
 
-void launch_conv_tc(const ConvArgs& a, cudaStream_t st);   // conv_tc.cu
-bool conv_tc_supported(const ConvArgs& a);
 
 namespace {
 constexpr int GX = 64;     // X-level granule (ids)
@@ -149,7 +147,7 @@ struct Runner {
     void conv(const ConvW& w, const float* x, int ldx, const Level& lin, const Opt& o) {
         ConvArgs p{};
         p.x = x; p.ldx = ldx; p.rows_in = lin.map.rows; p.cin = w.cin; p.in_slope = o.in_slope;
-        p.w = w.w; p.bias = w.bias; p.ldw = w.ldw; p.cout = w.cout;
+        p.w = w.w; p.bias = w.bias; p.ldw = w.ldw; p.cout = w.cout; p.wtc = w.wtc; p.tc_nt = w.tc_nt;
         p.ntaps = w.ntaps; memcpy(p.tap_off, w.tap_off, sizeof(p.tap_off)); p.min_off = w.min_off; p.span = w.span;
         p.rows_q = lin.map.rows; p.orow_mul = o.orow_mul; p.orow_add = o.orow_add;
         p.map = lin.map;
@@ -191,7 +189,7 @@ void run_decoder(Runner& R, const Level& LY, const float* s, float* d_wav, const
     const int RY = LY.map.rows;
     R.begin("dec.pre");
     float* p0 = c.dev.get<float>((size_t)RY * a.up_init);
-    { Runner::Opt o; o.y0 = p0; o.ldy0 = a.up_init; R.conv(v.conv_pre, s, a.inter, LY, o); }
+    { Runner::Opt o; o.y0 = p0; o.ldy0 = a.up_init; o.tc_ok = true; R.conv(v.conv_pre, s, a.inter, LY, o); }
     R.end();
     if (j.debug) { j.dbg["dec.pre"] = {p0, a.up_init}; j.dbg_level["dec.pre"] = 1; }
 
@@ -218,7 +216,7 @@ void run_decoder(Runner& R, const Level& LY, const float* s, float* d_wav, const
         }
         R.begin("dec.up" + std::to_string(i));
         for (int p = 0; p < st.u; p++) {
-            Runner::Opt o; o.in_slope = 0.1f; o.y0 = up; o.ldy0 = st.cout; o.orow_mul = st.u; o.orow_add = p;
+            Runner::Opt o; o.in_slope = 0.1f; o.y0 = up; o.ldy0 = st.cout; o.orow_mul = st.u; o.orow_add = p; o.tc_ok = true;
             R.conv(st.phase[p], cur, st.cin, Lin, o);
         }
         R.end();
@@ -491,16 +489,16 @@ void Job::run(float* d_out, size_t d_out_cap) {
     float* outb = C.dev.get<float>((size_t)RY * H);
     const int half = I / 2;
     for (const CouplingW& cp : V.flows) {
-        { Runner::Opt o; o.y0 = h; o.ldy0 = H; R.conv(cp.pre, s + cp.cond_off, I, LY, o); }
+        { Runner::Opt o; o.y0 = h; o.ldy0 = H; o.tc_ok = true; R.conv(cp.pre, s + cp.cond_off, I, LY, o); }
         const int n = (int)cp.in.size();
         for (int l = 0; l < n; l++) {
             { Runner::Opt o; o.act = ACT_GATE; o.y0 = acts; o.ldy0 = H; o.tc_ok = true; R.conv(cp.in[l], h, H, LY, o); }
-            Runner::Opt o;
+            Runner::Opt o; o.tc_ok = true;
             if (l < n - 1) { o.y0 = h; o.ldy0 = H; o.acc0 = 1; o.split = H; o.y1 = outb; o.ldy1 = H; o.acc1 = l > 0; }
             else { o.split = 0; o.y0 = outb; o.ldy0 = H; o.y1 = outb; o.ldy1 = H; o.acc1 = l > 0; }
             R.conv(cp.rs[l], acts, H, LY, o);
         }
-        { Runner::Opt o; o.y0 = s + cp.tgt_off; o.ldy0 = I; o.acc0 = 1; o.scale = -1.f; R.conv(cp.post, outb, H, LY, o); }
+        { Runner::Opt o; o.y0 = s + cp.tgt_off; o.ldy0 = I; o.acc0 = 1; o.scale = -1.f; o.tc_ok = true; R.conv(cp.post, outb, H, LY, o); }
     }
     (void)half;
     R.end();

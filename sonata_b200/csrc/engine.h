@@ -48,6 +48,7 @@ struct Arch {
 struct ConvW {
     float* w = nullptr;
     float* bias = nullptr;
+    float* wtc = nullptr; int tc_nt = 0;     // tcgen05 hi/lo swizzled weight images
     int cin = 0, cout = 0, ldw = 0, ntaps = 0;
     int tap_off[SB_MAX_TAPS] = {0};
     int min_off = 0, span = 0;
@@ -108,6 +109,7 @@ struct Voice {
 };
 
 Voice* load_voice(const std::string& config_path, int device);
+ConvW debug_make_conv(Voice& v, const float* w, const float* bias, int cout, int cin, int k, int dil);
 
 struct Region { std::string name; cudaEvent_t e0, e1; double flops = 0, bytes = 0; int launches = 0; float ms = 0; };
 

@@ -70,6 +70,24 @@ struct Uploader {
     }
 };
 
+int tc_tile_for(int cout) {
+    if (cout <= 128) return cout;
+    if (cout % 128 == 0) return 128;
+    if (cout % 96 == 0) return 96;
+    return 0;
+}
+
+// tcgen05 weight images for a finished ConvW whose [ntaps][cin][ldw] host copy is `wt`
+void add_tc_images(Uploader& U, ConvW& c, const std::vector<float>& wt) {
+    if (c.cin % 32 || c.cout % 32) return;
+    const int nt = tc_tile_for(c.cout);
+    if (!nt) return;
+    std::vector<float> img(conv_tc_weight_floats(c.cin, c.cout, c.ntaps, nt));
+    conv_tc_build_weights(wt.data(), c.ldw, c.cin, c.cout, c.ntaps, nt, img.data());
+    c.wtc = U.up(img);
+    c.tc_nt = nt;
+}
+
 // Conv1d weight [cout][cin][k] (+bias) -> ConvW with taps (t - (k-1)/2) * dil.
 // `perm_out`: output column n takes source row perm_out[n]; `perm_in` likewise for inputs.
 ConvW make_conv(Uploader& U, const std::vector<const HostTensor*>& ws, const std::vector<const HostTensor*>& bs,
@@ -114,6 +132,7 @@ ConvW make_conv(Uploader& U, const std::vector<const HostTensor*>& ws, const std
     }
     c.w = U.up(wt);
     c.bias = U.up(bt);
+    add_tc_images(U, c, wt);
     return c;
 }
 
@@ -155,6 +174,16 @@ uint32_t first_code_point(const std::string& s) {
 }
 
 }  // namespace
+
+// test hook: build a ConvW (both backends' weight layouts) from a raw [cout][cin][k] tensor
+ConvW debug_make_conv(Voice& v, const float* w, const float* bias, int cout, int cin, int k, int dil) {
+    HostTensor hw, hb;
+    hw.dims = {cout, cin, k}; hw.f.assign(w, w + (size_t)cout * cin * k);
+    hb.dims = {cout}; hb.f.assign(cout, 0.f);
+    if (bias) hb.f.assign(bias, bias + cout);
+    Uploader U{&v};
+    return make_conv(U, {&hw}, {&hb}, dil);
+}
 
 // VitsModelCommons::phonemes_to_input_ids + get_meta_ids (piper/src/lib.rs:173-179, 232-250)
 std::vector<long long> Voice::phonemes_to_ids(const char* utf8) const {
@@ -377,6 +406,7 @@ Voice* load_voice(const std::string& config_path, int device) {
                 c.span = mx - c.min_off;
                 for (int n = 0; n < c.cout; n++) bt[n] = b.f[n];
                 c.w = U.up(wt); c.bias = U.up(bt);
+                add_tc_images(U, c, wt);
                 st.phase.push_back(c);
             }
             C /= 2;

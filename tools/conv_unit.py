@@ -1,0 +1,81 @@
+"""Kernel unit check: one convolution through a backend vs torch conv1d (fp64 on CPU).
+Usage: python tools/conv_unit.py <backend> [quick]"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from sonata_b200 import _native as N  # noqa: E402
+
+
+def run_case(backend, rows, cin, cout, k, dil, slope=1.0, act=0, use_res=False, scale=1.0, acc=False, valid=None, seed=0):
+    lib = N.lib()
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(rows, cin, generator=g)
+    w = torch.randn(cout, cin, k, generator=g) / (cin * k) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    res = torch.randn(rows, cout, generator=g) if use_res else None
+    valid = rows if valid is None else valid
+    x[valid:] = 0
+    ycols = cout // 2 if act == 2 else cout
+    y0 = torch.randn(rows, ycols, generator=g) if acc else torch.zeros(rows, ycols)
+    y0[valid:] = 0
+    xin = torch.where(x > 0, x, x * slope).double()
+    ref = F.conv1d(xin.T[None], w.double(), b.double(), dilation=dil, padding=dil * (k - 1) // 2)[0].T
+    if act == 1:
+        ref = torch.relu(ref)
+    if act == 2:
+        ref = torch.tanh(ref[:, 0::2]) * torch.sigmoid(ref[:, 1::2])
+    if res is not None:
+        ref = ref + res.double()
+    ref = ref * scale
+    if acc:
+        ref = ref + y0.double()
+    ref[valid:] = 0
+    y = y0.clone().contiguous().numpy()
+    xn, wn, bn = x.contiguous().numpy(), w.contiguous().numpy(), b.contiguous().numpy()
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    rn = None if res is None else res.contiguous().numpy()
+    err = N.sb200_error()
+    rc = lib.sb200_debug_conv(0, backend, fp(xn), rows, cin, fp(wn), fp(bn), cout, k, dil, slope, act,
+                              None if rn is None else fp(rn), scale, 1 if acc else 0, fp(y), valid, C.byref(err))
+    if rc != 0:
+        msg = C.string_at(err.message).decode() if err.message else ""
+        return None, msg
+    e = float(np.abs(y - ref.numpy()).max())
+    return e, ""
+
+
+CASES = [
+    # rows, cin, cout, k, dil, slope, act, res, scale, acc, valid
+    (256, 32, 32, 1, 1, 1.0, 0, False, 1.0, False, None),
+    (256, 32, 32, 3, 1, 0.1, 0, True, 1.0, False, 200),
+    (512, 32, 32, 7, 12, 0.1, 0, True, 1 / 3, True, 450),
+    (384, 64, 64, 5, 6, 0.1, 0, True, 1.0, False, 300),
+    (256, 128, 128, 3, 2, 0.1, 0, True, 1.0, False, None),
+    (256, 192, 384, 5, 1, 1.0, 2, False, 1.0, False, 250),
+    (256, 192, 384, 1, 1, 1.0, 0, False, 1.0, True, None),
+    (256, 192, 96, 1, 1, 1.0, 0, False, -1.0, True, None),
+    (384, 256, 256, 11, 5, 0.1, 0, True, 1.0, False, 380),
+    (256, 192, 576, 1, 1, 1.0, 0, False, 1.0, False, None),
+    (256, 768, 192, 3, 1, 1.0, 0, False, 1.0, False, None),
+    (256, 192, 768, 3, 1, 1.0, 1, False, 1.0, False, None),
+]
+
+if __name__ == "__main__":
+    backend = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+    cases = CASES[:3] if len(sys.argv) > 2 else CASES
+    worst = 0.0
+    for c in cases:
+        e, msg = run_case(backend, *c)
+        print(f"backend {backend} case {c}: " + (f"max|err| {e:.3e}" if e is not None else f"ERROR {msg}"), flush=True)
+        if e is None:
+            sys.exit(2)
+        worst = max(worst, e)
+    print("worst", worst)
+    sys.exit(0 if worst < 1e-4 else 1)
