@@ -90,6 +90,9 @@ void launch_randn(float* out, long long n, unsigned long long seed, unsigned lon
 void launch_scale_copy2(const float* eps, float s, float* z, RowMap map, cudaStream_t st);   // z[r][0..1] = eps*s
 void launch_fill_zero(float* p, long long n, cudaStream_t st);
 
+// launch-configuration errors are not sticky and would otherwise be lost: throw immediately
+void check_launch(const char* what);
+
 extern unsigned long long g_launch_count;   // kernels launched by this library (host-side counter)
 
 }  // namespace sb200

@@ -194,6 +194,7 @@ void launch_cfg(const ConvArgs& a, cudaStream_t st) {
     dim3 grid((a.rows_q + BM - 1) / BM, a.ldw / BN);
     kern<<<grid, 256, smem, st>>>(a);
     g_launch_count++;
+    check_launch("conv");
 }
 
 }  // namespace

@@ -1,36 +1,45 @@
-// tcgen05 implicit-GEMM Conv1d with error-compensated 3xTF32 (sm_100a).
+// tcgen05 implicit-GEMM Conv1d with a 2-term BF16 split ("bf16x2", fp32 accumulate in TMEM), sm_100a.
 //
 // Same contract as conv_simt.cu (ConvArgs): out[q][n] = epi(bias[n] + sum_t sum_c f(x[q+off_t][c]) w[t][c][n]).
-// GEMM view per CTA: D[128 rows x NT cols] (fp32, in TMEM) += A_t[128 x 32] . W_t[32 x NT] over
-// (32-channel K-block, tap).  A plain TF32 MMA misses the 1e-3 waveform tolerance (measured 1.9e-3 /
-// 3.6e-3 on the medium / high voice), so every operand is split v = hi + lo with hi = v & 0xffffe000
-// and three MMAs accumulate hi*hi + lo*hi + hi*lo  (error ~2e-6 end to end, oracle-level).
+// GEMM view per tile: D[128 rows x NT cols] (fp32, TMEM) += A_t[128 x 32] . W_t[32 x NT] over (32-channel
+// K-block, tap).
+//
+// Precision.  A single reduced-precision MMA misses the 1e-3 waveform tolerance (TF32: 1.9e-3 / 3.6e-3 on
+// the medium / high voice).  Every operand is therefore split  v = hi + lo,  hi = bf16_rn(v),
+// lo = bf16_rn(v - hi)  (16 mantissa bits together) and three MMAs accumulate  hi*hi + lo*hi + hi*lo.
+// End-to-end waveform error 2e-5 / 3.5e-5 (oracle emulation) -- the same as a 3xTF32 split, which was
+// implemented first and needs TWICE the MMA instructions (K = 8 per tf32 MMA vs 16 per bf16 MMA).  That
+// matters because a measured ~80-cycle floor applies to every M=128 SS-mode MMA whatever its N
+// (tools/micro/mma_bench.cu: 81.4 / 80.1 / 79.6 cycles at N = 32 / 64 / 128), and the hot layers here
+// have N = C_out = 32..128.
 //
 // Data path (no tensor maps needed):
-//   * activations: producer warps read the (128 + span)-row WINDOW of the K-block from HBM with
-//     coalesced 128-bit loads, apply the leaky-ReLU prologue, split hi/lo and store both images in the
+//   * activations: producer warps read the (128 + span)-row WINDOW of a K-block from HBM with coalesced
+//     128-bit loads (the whole stage in flight before first use), apply the leaky-ReLU prologue, split
+//     hi/lo and store ONE image row per time step:  [hi: 32 ch bf16 | lo: 32 ch bf16] = 128 B, in the
 //     canonical K-major SWIZZLE_128B layout (row r at r*128 B, 16-B chunk c at (c ^ (r & 7))).  A tap is
-//     just a descriptor whose start address is shifted by off_t rows, so a k-tap conv stages its input
-//     ONCE and issues k x 12 MMAs on it;
-//   * weights: pre-split, pre-swizzled tile images written at voice-load time; one cp.async.bulk
-//     (UBLKCP) per (K-block, tap) stage into an mbarrier-tracked ring;
-//   * MMA: one elected thread issues tcgen05.mma.kind::tf32 (UTCxMMA), tcgen05.commit frees ring slots;
-//   * epilogue: tcgen05.ld 32x32b.x32 (LDTM) -> bias / gate / residual / scale / accumulate -> HBM.
-// Warp roles: w0 = MMA issuer + TMEM alloc, w1 = weight producer, w2..7 = activation producers,
-// all 8 warps run the epilogue.  Several CTAs are resident per SM so one tile's epilogue overlaps
-// another's loads and MMAs.  Every mbarrier wait carries a watchdog that traps instead of hanging.
+//     only a descriptor whose start address is shifted by off_t rows (the swizzle is a function of the
+//     absolute smem address), so a k-tap conv stages its input once and issues k x 6 MMAs on it;
+//   * weights: pre-split, pre-swizzled [hi|lo] tile images written at voice-load time; one
+//     cp.async.bulk (UBLKCP) per (K-block, tap) stage, resident in smem for the whole CTA when they fit;
+//   * MMA: tcgen05.mma.kind::f16 (UTCHMMA), issued from warp-uniform code under elect.sync;
+//     tcgen05.commit releases ring slots / publishes the accumulator;
+//   * epilogue: tcgen05.ld 32x32b.x32 (LDTM) -> bias / gate / residual / scale / accumulate -> HBM, with
+//     the residual / read-modify-write operands prefetched before the accumulator is awaited.
+// Persistent CTAs (one per SM) walk tiles blockIdx.x, +gridDim.x, ...; three mbarrier pipelines
+// (activation ring, weight ring, double-buffered TMEM accumulator) run across tile boundaries.
+// Warps: w0 MMA issuer (+TMEM alloc), w1 weight producer, w2-5 / w6-9 two activation-producer groups
+// (alternating stages), w10-13 epilogue.  Every mbarrier wait carries a watchdog that traps instead of
+// hanging the GPU.
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include <stdio.h>
-#include <string.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace sb200 {
 
 namespace {
-
-constexpr int TC_THREADS = 256;
-constexpr int TC_PRODUCERS = 192;     // warps 2..7
-constexpr int TC_MAX_WSTAGES = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -61,8 +70,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
         if (t0 == 0) t0 = now;
         if (now - t0 > 2000000000ull) {   // 2 s: a pipeline bug must fail loudly, never hang the GPU
-            printf("conv_tc: mbarrier watchdog (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y,
-                   threadIdx.x, bar, parity);
+            printf("conv_tc: mbarrier watchdog (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar,
+                   parity);
             asm volatile("trap;");
         }
     }
@@ -77,25 +86,22 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
-}
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
-// start>>4 | LBO(1)<<16 | SBO(1024>>4)<<32 | version 1<<46 | base_offset<<49 | layout SWIZZLE_128B(2)<<61
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int mode = 0) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    if (mode == 1) d |= (uint64_t)((saddr >> 7) & 7) << 49;   // 'matrix base offset' variant (experiment)
-    d |= (uint64_t)2 << 61;
-    return d;
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -109,45 +115,58 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// pack (hi, lo) halves of two consecutive channels: returns the hi pair, writes the lo pair
+__device__ __forceinline__ uint32_t split2(float a, float b, uint32_t& lo) {
+    const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+    const __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha));
+    const __nv_bfloat16 lb = __float2bfloat16_rn(b - __bfloat162float(hb));
+    lo = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
+    return (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+}
 
 struct TcLaunch {
-    int nt;          // columns per CTA (multiple of 32, <= 256)
+    int nt;          // columns per CTA tile (multiple of 32, <= 256)
     int win;         // window rows (multiple of 8)
-    int na;          // activation buffers (1 or 2)
-    int ws;          // weight ring stages
-    int tmem_cols;   // power of two >= 32
+    int na;          // activation ring stages
+    int ws;          // weight ring stages (or all (K-block, tap) stages when resident)
+    int resident;    // weights loaded once per CTA (single n-tile, short K loop)
+    int tmem_cols;   // power of two >= 2*nt (two accumulator stages)
+    int ntiles_m, ntiles_n;
     uint32_t idesc;
-    int desc_mode;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a, const TcLaunch L) {
+constexpr int TC_MAXCH = 7;             // 32-B input pieces per producer thread per stage (win <= 224 rows)
+constexpr int TC_GROUP = 128;           // threads per producer group
+constexpr int TC_EPI0 = 10;             // first epilogue warp
+constexpr int TC2_THREADS = 448;        // w0 MMA, w1 weights, w2-5 / w6-9 activation groups, w10-13 epilogue
+constexpr int TC_MAX_ASTAGES = 6;
+constexpr int TC_MAX_WRING = 44;        // barrier slots for the weight ring / resident set
+
+__global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs a, const TcLaunch L) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: [A hi/lo x na][W ring x ws][barriers]
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const uint32_t a_img = (uint32_t)L.win * 128u;              // bytes of one hi (or lo) window image
-    const uint32_t a_buf = ((2u * a_img + 1023u) / 1024u) * 1024u;
-    const uint32_t w_img = (uint32_t)L.nt * 128u;
-    const uint32_t w_stage = 2u * w_img;
+    const uint32_t a_buf = (uint32_t)L.win * 128u;              // one [hi|lo] window image
+    const uint32_t w_stage = (uint32_t)L.nt * 128u;             // one [hi|lo] weight tile image
     uint8_t* A0 = smem;
     uint8_t* W0 = A0 + (size_t)L.na * a_buf;
     uint64_t* bars = reinterpret_cast<uint64_t*>(W0 + (size_t)L.ws * w_stage);
-    // barrier indices
-    uint64_t* w_full = bars;                          // [ws]
-    uint64_t* w_empty = bars + TC_MAX_WSTAGES;        // [ws]
-    uint64_t* a_full = bars + 2 * TC_MAX_WSTAGES;     // [2]
-    uint64_t* a_empty = a_full + 2;                   // [2]
-    uint64_t* acc_full = a_empty + 2;                 // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+    uint64_t* w_full = bars;                               // [TC_MAX_WRING]
+    uint64_t* w_empty = w_full + TC_MAX_WRING;             // [TC_MAX_WRING]
+    uint64_t* a_full = w_empty + TC_MAX_WRING;             // [TC_MAX_ASTAGES]
+    uint64_t* a_empty = a_full + TC_MAX_ASTAGES;           // [TC_MAX_ASTAGES]
+    uint64_t* acc_full = a_empty + TC_MAX_ASTAGES;         // [2]
+    uint64_t* acc_empty = acc_full + 2;                    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q0 = blockIdx.x * 128;
-    const int n0 = blockIdx.y * L.nt;
     const int nkb = a.cin / 32;
+    const int total_tiles = L.ntiles_m * L.ntiles_n;
+    const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (tid == 0) {
         for (int s = 0; s < L.ws; s++) { mbar_init(smem_u32(&w_full[s]), 1); mbar_init(smem_u32(&w_empty[s]), 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(smem_u32(&a_full[s]), TC_PRODUCERS); mbar_init(smem_u32(&a_empty[s]), 1); }
-        mbar_init(smem_u32(acc_full), 1);
+        for (int s = 0; s < L.na; s++) { mbar_init(smem_u32(&a_full[s]), TC_GROUP); mbar_init(smem_u32(&a_empty[s]), 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(smem_u32(&acc_full[s]), 1); mbar_init(smem_u32(&acc_empty[s]), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -162,165 +181,226 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
 
     if (warp == 0) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            int ws = 0; uint32_t wpar = 0;
-            for (int kb = 0; kb < nkb; kb++) {
-                const int buf = kb % L.na;
-                mbar_wait(smem_u32(&a_full[buf]), (uint32_t)((kb / L.na) & 1));
+        // The WHOLE warp walks the loop with warp-uniform values (descriptors live in uniform registers, no
+        // R2UR waterfall loops); only the tcgen05 instructions sit under elect.sync.
+        // K-major SWIZZLE_128B descriptor (cute::UMMA::SmemDescriptor v1): start>>4 | LBO 1<<16 | SBO (1024>>4)<<32 |
+        // version 1<<46 | layout SWIZZLE_128B 2<<61; "matrix base offset" stays 0 even for row-shifted starts
+        // (measured: a non-zero base offset breaks every k > 1 case).
+        const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+        int it = 0, wit = 0;
+        for (int tl = 0; tl < my_tiles; tl++) {
+            const int acc = tl & 1;
+            mbar_wait(smem_u32(&acc_empty[acc]), (uint32_t)(((tl >> 1) & 1) ^ 1));
+            tc_fence_after();
+            const uint32_t dcol = tmem_base + (uint32_t)(acc * L.nt);
+            for (int kb = 0; kb < nkb; kb++, it++) {
+                const int as = it % L.na;
+                mbar_wait(smem_u32(&a_full[as]), (uint32_t)((it / L.na) & 1));
                 tc_fence_after();
-                const uint32_t ahi = smem_u32(A0 + (size_t)buf * a_buf);
-                const uint32_t alo = ahi + a_img;
-                for (int t = 0; t < a.ntaps; t++) {
+                const uint32_t aimg = smem_u32(A0 + (size_t)as * a_buf) >> 4;
+                for (int t = 0; t < a.ntaps; t++, wit++) {
+                    int ws; uint32_t wpar;
+                    if (L.resident) { ws = kb * a.ntaps + t; wpar = 0; }
+                    else { ws = wit % L.ws; wpar = (uint32_t)((wit / L.ws) & 1); }
                     mbar_wait(smem_u32(&w_full[ws]), wpar);
                     tc_fence_after();
-                    const uint32_t whi = smem_u32(W0 + (size_t)ws * w_stage);
-                    const uint32_t wlo = whi + w_img;
-                    const uint32_t rowoff = (uint32_t)(a.tap_off[t] - a.min_off) * 128u;
+                    const uint32_t wimg = smem_u32(W0 + (size_t)ws * w_stage) >> 4;
+                    const uint32_t arow = aimg + (uint32_t)(a.tap_off[t] - a.min_off) * 8u;      // rows * 128 B >> 4
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; k4++) {
-                        const uint64_t dah = make_desc(ahi + rowoff + k4 * 32, L.desc_mode);
-                        const uint64_t dal = make_desc(alo + rowoff + k4 * 32, L.desc_mode);
-                        const uint64_t dwh = make_desc(whi + k4 * 32);
-                        const uint64_t dwl = make_desc(wlo + k4 * 32);
-                        const uint32_t first = (kb | t | k4) ? 1u : 0u;
-                        tc_mma_tf32(tmem_base, dah, dwh, L.idesc, first);
-                        tc_mma_tf32(tmem_base, dal, dwh, L.idesc, 1u);
-                        tc_mma_tf32(tmem_base, dah, dwl, L.idesc, 1u);
+                        for (int ks = 0; ks < 2; ks++) {                 // two K = 16 steps inside the 64-B hi half
+                            const uint64_t dah = desc_hi | (uint64_t)(arow + ks * 2);
+                            const uint64_t dal = desc_hi | (uint64_t)(arow + 4 + ks * 2);   // lo half starts at byte 64
+                            const uint64_t dwh = desc_hi | (uint64_t)(wimg + ks * 2);
+                            const uint64_t dwl = desc_hi | (uint64_t)(wimg + 4 + ks * 2);
+                            tc_mma_bf16(dcol, dah, dwh, L.idesc, (kb | t | ks) ? 1u : 0u);
+                            tc_mma_bf16(dcol, dal, dwh, L.idesc, 1u);
+                            tc_mma_bf16(dcol, dah, dwl, L.idesc, 1u);
+                        }
+                        if (!L.resident) tc_commit(smem_u32(&w_empty[ws]));   // slot reusable once these MMAs retire
                     }
-                    tc_commit(smem_u32(&w_empty[ws]));     // ring slot reusable once these MMAs retire
-                    if (++ws == L.ws) { ws = 0; wpar ^= 1; }
+                    __syncwarp();
                 }
-                tc_commit(smem_u32(&a_empty[buf]));
+                if (elect_one()) tc_commit(smem_u32(&a_empty[as]));
+                __syncwarp();
             }
-            tc_commit(smem_u32(acc_full));
+            if (elect_one()) tc_commit(smem_u32(&acc_full[acc]));
+            __syncwarp();
         }
-        __syncwarp();
     } else if (warp == 1) {
         // ===================== weight producer =====================
         if (lane == 0) {
-            int ws = 0; uint32_t wpar = 0;
-            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wtc) +
-                                  (size_t)blockIdx.y * nkb * a.ntaps * w_stage;
-            for (int it = 0; it < nkb * a.ntaps; it++) {
-                if (it >= L.ws) mbar_wait(smem_u32(&w_empty[ws]), wpar ^ 1);
-                mbar_expect_tx(smem_u32(&w_full[ws]), w_stage);
-                bulk_g2s(smem_u32(W0 + (size_t)ws * w_stage), wsrc + (size_t)it * w_stage, w_stage, smem_u32(&w_full[ws]));
-                if (++ws == L.ws) { ws = 0; wpar ^= 1; }
+            const int per_tile = nkb * a.ntaps;
+            if (L.resident) {
+                const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wtc);
+                for (int s = 0; s < per_tile; s++) {
+                    mbar_expect_tx(smem_u32(&w_full[s]), w_stage);
+                    bulk_g2s(smem_u32(W0 + (size_t)s * w_stage), wsrc + (size_t)s * w_stage, w_stage, smem_u32(&w_full[s]));
+                }
+            } else {
+                int wit = 0;
+                for (int tl = 0; tl < my_tiles; tl++) {
+                    const int tg = (int)blockIdx.x + tl * (int)gridDim.x;
+                    const int n_tile = tg % L.ntiles_n;
+                    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wtc) + (size_t)n_tile * per_tile * w_stage;
+                    for (int i = 0; i < per_tile; i++, wit++) {
+                        const int ws = wit % L.ws;
+                        mbar_wait(smem_u32(&w_empty[ws]), (uint32_t)(((wit / L.ws) & 1) ^ 1));
+                        mbar_expect_tx(smem_u32(&w_full[ws]), w_stage);
+                        bulk_g2s(smem_u32(W0 + (size_t)ws * w_stage), wsrc + (size_t)i * w_stage, w_stage, smem_u32(&w_full[ws]));
+                    }
+                }
             }
         }
         __syncwarp();
-    } else {
-        // ===================== activation producers (192 threads) =====================
-        const int pt = tid - 64;
-        const int nchunk = L.win * 8;
-        const int rbase = q0 + a.min_off;
+    } else if (warp < TC_EPI0) {
+        // ===================== activation producers: two groups of 128 threads, alternating stages ==========
+        const int grp = (warp - 2) >> 2;
+        const int gt = tid - 64 - grp * TC_GROUP;
+        const int npiece = L.win * 4;                  // 32-B pieces (8 channels) per stage
         const float slope = a.in_slope;
-        for (int kb = 0; kb < nkb; kb++) {
-            const int buf = kb % L.na;
-            if (kb >= L.na) mbar_wait(smem_u32(&a_empty[buf]), (uint32_t)(((kb / L.na) - 1) & 1));
-            uint8_t* hi = A0 + (size_t)buf * a_buf;
-            uint8_t* lo = hi + a_img;
-            const float* xk = a.x + kb * 32;
-            for (int base = pt; base < nchunk; base += TC_PRODUCERS * 4) {
-                float4 v[4];
+        int it = 0;
+        for (int tl = 0; tl < my_tiles; tl++) {
+            const int tg = (int)blockIdx.x + tl * (int)gridDim.x;
+            const int q0 = (tg / L.ntiles_n) * 128;
+            const int rbase = q0 + a.min_off;
+            for (int kb = 0; kb < nkb; kb++, it++) {
+                if ((it & 1) != grp) continue;
+                const int as = it % L.na;
+                const float* xk = a.x + kb * 32;
+                float4 v[TC_MAXCH][2];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int idx = base + u * TC_PRODUCERS;
-                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (idx < nchunk) {
-                        const int gr = rbase + (idx >> 3);
-                        if (gr >= 0 && gr < a.rows_in)
-                            v[u] = *reinterpret_cast<const float4*>(xk + (size_t)gr * a.ldx + (idx & 7) * 4);
+                for (int u = 0; u < TC_MAXCH; u++) {          // the whole stage in flight before the first use
+                    const int idx = gt + u * TC_GROUP;
+                    v[u][0] = v[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (idx < npiece) {
+                        const int gr = rbase + (idx >> 2);
+                        if (gr >= 0 && gr < a.rows_in) {
+                            const float4* src = reinterpret_cast<const float4*>(xk + (size_t)gr * a.ldx + (idx & 3) * 8);
+                            v[u][0] = src[0];
+                            v[u][1] = src[1];
+                        }
                     }
                 }
+                mbar_wait(smem_u32(&a_empty[as]), (uint32_t)(((it / L.na) & 1) ^ 1));
+                uint8_t* img = A0 + (size_t)as * a_buf;
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int idx = base + u * TC_PRODUCERS;
-                    if (idx >= nchunk) continue;
-                    const int r = idx >> 3, c = idx & 7;
-                    float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-                    float h[4], l[4];
+                for (int u = 0; u < TC_MAXCH; u++) {
+                    const int idx = gt + u * TC_GROUP;
+                    if (idx >= npiece) continue;
+                    const int r = idx >> 2, c = idx & 3;
+                    float e[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const float f = e[i] > 0.f ? e[i] : e[i] * slope;
-                        h[i] = __uint_as_float(__float_as_uint(f) & 0xffffe000u);
-                        l[i] = f - h[i];
-                    }
-                    const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
-                    *reinterpret_cast<float4*>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
-                    *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+                    for (int i = 0; i < 8; i++) e[i] = e[i] > 0.f ? e[i] : e[i] * slope;
+                    uint4 hi, lo;
+                    hi.x = split2(e[0], e[1], lo.x);
+                    hi.y = split2(e[2], e[3], lo.y);
+                    hi.z = split2(e[4], e[5], lo.z);
+                    hi.w = split2(e[6], e[7], lo.w);
+                    const uint32_t rowb = (uint32_t)r * 128u;
+                    const uint32_t sw = (uint32_t)(r & 7);
+                    *reinterpret_cast<uint4*>(img + rowb + (((uint32_t)c ^ sw) << 4)) = hi;
+                    *reinterpret_cast<uint4*>(img + rowb + (((uint32_t)(c + 4) ^ sw) << 4)) = lo;
                 }
+                fence_async_smem();                       // generic-proxy stores -> visible to the tensor core
+                mbar_arrive(smem_u32(&a_full[as]));
             }
-            fence_async_smem();                       // generic-proxy stores -> visible to the tensor core
-            mbar_arrive(smem_u32(&a_full[buf]));
         }
-    }
-
-    // ===================== epilogue (all 8 warps) =====================
-    mbar_wait(smem_u32(acc_full), 0);
-    tc_fence_after();
-    {
-        const int quad = warp & 3, halfsel = warp >> 2;
+    } else {
+        // ===================== epilogue (warps 10..13, one TMEM lane quadrant each) =====================
+        // Residual / read-modify-write operands of chunk 0 are prefetched BEFORE the accumulator is awaited.
+        const int quad = warp & 3;
         const int row = quad * 32 + lane;
-        const int q = q0 + row;
-        const bool inrange = q < a.rows_q;
-        const bool valid = inrange && row_valid(a.map, q);
-        const size_t orow = (size_t)q * a.orow_mul + a.orow_add;
-        for (int ch = halfsel; ch < L.nt / 32; ch += 2) {
-            float o[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ch * 32), o);
-            const int n = n0 + ch * 32;
-            if (!inrange || n >= a.cout) continue;
-            if (a.bias) {
+        const int nch = L.nt / 32;
+        const bool gate = a.act == ACT_GATE;
+        for (int tl = 0; tl < my_tiles; tl++) {
+            const int tg = (int)blockIdx.x + tl * (int)gridDim.x;
+            const int q = (tg / L.ntiles_n) * 128 + row;
+            const int n0 = (tg % L.ntiles_n) * L.nt;
+            const int acc = tl & 1;
+            const bool inrange = q < a.rows_q;
+            const bool valid = inrange && row_valid(a.map, q);
+            const size_t orow = (size_t)q * a.orow_mul + a.orow_add;
+            float rn[32], pn[32];
+            auto prefetch = [&](int ch) {
+                const int n = n0 + ch * 32;
+                const bool live = valid && n < a.cout && !gate;
+                if (a.res) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 b = *reinterpret_cast<const float4*>(a.bias + n + j);
-                    o[j] += b.x; o[j + 1] += b.y; o[j + 2] += b.z; o[j + 3] += b.w;
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (live) r = *reinterpret_cast<const float4*>(a.res + orow * a.ldres + n + j);
+                        rn[j] = r.x; rn[j + 1] = r.y; rn[j + 2] = r.z; rn[j + 3] = r.w;
+                    }
                 }
-            }
-            if (a.act == ACT_GATE) {
-                float* dst = a.y0 + orow * a.ldy0 + (n >> 1);
+                const bool lo_side = n < a.split;
+                if (lo_side ? a.acc0 : a.acc1) {
+                    const float* src = lo_side ? a.y0 + orow * a.ldy0 + n : a.y1 + orow * a.ldy1 + (n - a.split);
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    float g[4];
-#pragma unroll
-                    for (int e = 0; e < 4; e++)
-                        g[e] = valid ? tanhf(o[2 * (j + e)]) * (1.f / (1.f + expf(-o[2 * (j + e) + 1]))) * a.scale : 0.f;
-                    *reinterpret_cast<float4*>(dst + j) = make_float4(g[0], g[1], g[2], g[3]);
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (live) r = *reinterpret_cast<const float4*>(src + j);
+                        pn[j] = r.x; pn[j + 1] = r.y; pn[j + 2] = r.z; pn[j + 3] = r.w;
+                    }
                 }
-                continue;
-            }
-            if (a.act == ACT_RELU) {
-#pragma unroll
-                for (int j = 0; j < 32; j++) o[j] = fmaxf(o[j], 0.f);
-            }
-            if (a.res && valid) {
-                const float* rp = a.res + orow * a.ldres + n;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 r = *reinterpret_cast<const float4*>(rp + j);
-                    o[j] += r.x; o[j + 1] += r.y; o[j + 2] += r.z; o[j + 3] += r.w;
+            };
+            prefetch(0);
+            mbar_wait(smem_u32(&acc_full[acc]), (uint32_t)((tl >> 1) & 1));
+            tc_fence_after();
+            for (int ch = 0; ch < nch; ch++) {
+                float o[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * L.nt + ch * 32), o);
+                if (ch == nch - 1) {          // accumulator fully read: hand it back to the MMA warp
+                    tc_fence_before();
+                    mbar_arrive(smem_u32(&acc_empty[acc]));
                 }
-            }
+                const int n = n0 + ch * 32;
+                const bool lo_side = n < a.split;
+                const int accum = lo_side ? a.acc0 : a.acc1;
+                if (ch > 0) prefetch(ch);
+                if (!inrange || n >= a.cout) continue;
+                if (a.bias) {
 #pragma unroll
-            for (int j = 0; j < 32; j++) o[j] *= a.scale;
-            float* dst; int accum;
-            if (n < a.split) { dst = a.y0 + orow * a.ldy0 + n; accum = a.acc0; }
-            else { dst = a.y1 + orow * a.ldy1 + (n - a.split); accum = a.acc1; }
-            if (accum) {
-                if (!valid) continue;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 p = *reinterpret_cast<const float4*>(dst + j);
-                    o[j] += p.x; o[j + 1] += p.y; o[j + 2] += p.z; o[j + 3] += p.w;
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b = *reinterpret_cast<const float4*>(a.bias + n + j);
+                        o[j] += b.x; o[j + 1] += b.y; o[j + 2] += b.z; o[j + 3] += b.w;
+                    }
                 }
-            } else if (!valid) {
+                if (gate) {
+                    float* dst = a.y0 + orow * a.ldy0 + (n >> 1);
 #pragma unroll
-                for (int j = 0; j < 32; j++) o[j] = 0.f;
+                    for (int j = 0; j < 16; j += 4) {
+                        float g[4];
+#pragma unroll
+                        for (int e = 0; e < 4; e++)
+                            g[e] = valid ? tanhf(o[2 * (j + e)]) * (1.f / (1.f + expf(-o[2 * (j + e) + 1]))) * a.scale : 0.f;
+                        *reinterpret_cast<float4*>(dst + j) = make_float4(g[0], g[1], g[2], g[3]);
+                    }
+                    continue;
+                }
+                if (a.act == ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) o[j] = fmaxf(o[j], 0.f);
+                }
+                if (a.res && valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) o[j] += rn[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j++) o[j] *= a.scale;
+                float* dst = lo_side ? a.y0 + orow * a.ldy0 + n : a.y1 + orow * a.ldy1 + (n - a.split);
+                if (accum) {
+                    if (!valid) continue;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) o[j] += pn[j];
+                } else if (!valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) o[j] = 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
             }
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
         }
     }
     tc_fence_before();
@@ -334,24 +414,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
 bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem) {
     if (!a.wtc || a.tc_nt <= 0) return false;
     L.nt = a.tc_nt;
-    { const char* e = getenv("SB200_TC_DESC_MODE"); L.desc_mode = e ? atoi(e) : 0; }
     L.win = (128 + a.span + 7) & ~7;
+    if (L.win * 4 > TC_MAXCH * TC_GROUP) return false;
     L.tmem_cols = 32;
-    while (L.tmem_cols < L.nt) L.tmem_cols <<= 1;
-    L.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(L.nt >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const size_t a_buf = ((size_t)2 * L.win * 128 + 1023) / 1024 * 1024;
-    const size_t w_stage = (size_t)2 * L.nt * 128;
-    const int nkb = a.cin / 32;
-    const int iters = nkb * a.ntaps;
-    // prefer small footprints (2-3 CTAs per SM) for short K loops, deeper buffering for long ones
-    L.na = nkb > 1 ? 2 : 1;
-    L.ws = iters < TC_MAX_WSTAGES ? iters : TC_MAX_WSTAGES;
-    auto total = [&]() { return (size_t)L.na * a_buf + (size_t)L.ws * w_stage + 256 + 1024; };
-    while (total() > 200 * 1024 && L.ws > 2) L.ws--;
-    if (total() > 200 * 1024 && L.na > 1) L.na = 1;
-    if (total() > 220 * 1024) return false;
-    smem = total();
+    while (L.tmem_cols < 2 * L.nt) L.tmem_cols <<= 1;
+    if (L.tmem_cols > 512) return false;
+    // kind::f16 instruction descriptor: D fp32 (1<<4), A = B = BF16 (1<<7, 1<<10), K-major both, N>>3, M>>4
+    L.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(L.nt >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    L.ntiles_m = (a.rows_q + 127) / 128;
+    L.ntiles_n = (a.cout + L.nt - 1) / L.nt;
+    const size_t a_buf = (size_t)L.win * 128;
+    const size_t w_stage = (size_t)L.nt * 128;
+    const int per_tile = (a.cin / 32) * a.ntaps;
+    const size_t budget = 225 * 1024 - 2048;
+    const size_t bar_bytes = (2 * TC_MAX_WRING + 2 * TC_MAX_ASTAGES + 4) * 8 + 16;
+    L.resident = (L.ntiles_n == 1 && per_tile <= TC_MAX_WRING && per_tile * w_stage + 3 * a_buf + bar_bytes <= budget) ? 1 : 0;
+    L.ws = L.resident ? per_tile : (per_tile < 6 ? per_tile : 6);
+    if (!L.resident && L.ws < 2) L.ws = 2;
+    auto total = [&]() { return (size_t)L.na * a_buf + (size_t)L.ws * w_stage + bar_bytes; };
+    L.na = TC_MAX_ASTAGES;
+    while (L.na > 2 && total() > budget) L.na--;
+    while (!L.resident && L.ws > 2 && total() > budget) L.ws--;
+    if (total() > budget) return false;
+    smem = total() + 2048;
     return true;
+}
+
+uint16_t bf16_rn_host(float f) {
+    uint32_t b; memcpy(&b, &f, 4);
+    b += 0x7fffu + ((b >> 16) & 1u);
+    return (uint16_t)(b >> 16);
+}
+float bf16_to_float_host(uint16_t h) {
+    uint32_t b = (uint32_t)h << 16; float f; memcpy(&f, &b, 4); return f;
 }
 
 }  // namespace
@@ -362,6 +457,12 @@ bool conv_tc_supported(const ConvArgs& a) {
     return plan(a, L, smem);
 }
 
+static int tc_num_sms() {
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+    return n;
+}
+
 void launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     TcLaunch L; size_t smem;
     if (!plan(a, L, smem)) { launch_conv_simt(a, st); return; }
@@ -370,40 +471,42 @@ void launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
         cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_done = true;
     }
-    dim3 grid((a.rows_q + 127) / 128, (a.cout + L.nt - 1) / L.nt);
-    conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(a, L);
+    const int tiles = L.ntiles_m * L.ntiles_n;
+    const int grid = tiles < tc_num_sms() ? tiles : tc_num_sms();
+    conv_tc_kernel<<<grid, TC2_THREADS, smem, st>>>(a, L);
     g_launch_count++;
+    check_launch("conv_tc");
 }
 
-// Host-side weight image builder: [n-tile][K-block][tap]{hi image, lo image}, each image nt rows x 128 B
-// in the K-major SWIZZLE_128B layout the tensor core reads (row n at n*128, chunk c at (c ^ (n & 7))).
+// Host-side weight image builder: [n-tile][K-block][tap] images of nt rows x 128 B, row n =
+// [hi: 32 ch bf16 | lo: 32 ch bf16] in the K-major SWIZZLE_128B layout (16-B chunk c at (c ^ (n & 7))).
+// Sizes are in floats (4-byte units) because the voice arena is a float arena.
 size_t conv_tc_weight_floats(int cin, int cout, int ntaps, int nt) {
     const int ntiles = (cout + nt - 1) / nt;
-    return (size_t)ntiles * (cin / 32) * ntaps * 2 * nt * 32;
+    return (size_t)ntiles * (cin / 32) * ntaps * nt * 32;
 }
 
 void conv_tc_build_weights(const float* wt /*[ntaps][cin][ldw]*/, int ldw, int cin, int cout, int ntaps, int nt,
                            float* out) {
     const int ntiles = (cout + nt - 1) / nt;
     const int nkb = cin / 32;
-    size_t o = 0;
+    uint16_t* o16 = reinterpret_cast<uint16_t*>(out);
+    size_t o = 0;   // in bf16 elements
     for (int j = 0; j < ntiles; j++)
         for (int kb = 0; kb < nkb; kb++)
             for (int t = 0; t < ntaps; t++) {
-                float* hi = out + o;
-                float* lo = hi + (size_t)nt * 32;
+                uint16_t* img = o16 + o;
                 for (int n = 0; n < nt; n++)
                     for (int c = 0; c < 32; c++) {
                         const int col = j * nt + n;
                         const float v = col < cout ? wt[((size_t)t * cin + kb * 32 + c) * ldw + col] : 0.f;
-                        uint32_t bits; memcpy(&bits, &v, 4);
-                        bits &= 0xffffe000u;
-                        float h; memcpy(&h, &bits, 4);
-                        const size_t idx = (size_t)n * 32 + (size_t)(((c >> 2) ^ (n & 7)) << 2) + (c & 3);
-                        hi[idx] = h;
-                        lo[idx] = v - h;
+                        const uint16_t h = bf16_rn_host(v);
+                        const uint16_t l = bf16_rn_host(v - bf16_to_float_host(h));
+                        const int ch = c >> 3, e = c & 7;                        // 16-B chunk (8 bf16) and element
+                        img[(size_t)n * 64 + (size_t)((ch ^ (n & 7)) << 3) + e] = h;
+                        img[(size_t)n * 64 + (size_t)(((ch + 4) ^ (n & 7)) << 3) + e] = l;
                     }
-                o += (size_t)2 * nt * 32;
+                o += (size_t)nt * 64;
             }
 }
 

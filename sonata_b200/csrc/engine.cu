@@ -10,6 +10,11 @@
 
 namespace sb200 {
 
+void check_launch(const char* what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw Error(19, std::string("CUDA launch failed (") + what + "): " + cudaGetErrorString(e));
+}
+
 
 namespace {
 constexpr int GX = 64;     // X-level granule (ids)
@@ -380,6 +385,8 @@ void Job::run(float* d_out, size_t d_out_cap) {
     }
 
     // ---------------- text encoder ----------------
+    // (kept on the fp32 CUDA-core kernel: the duration predictor reads x, and ceil(duration) is a cliff --
+    //  3xTF32 moves logw by ~1e-4, fp32 by ~5e-6)
     R.begin("enc");
     launch_embed(d_ids_rows, V.emb, sqrtf((float)H), xa, RX, H, st);
     R.count(0, 4.0 * LX.valid_rows * H);
@@ -396,7 +403,7 @@ void Job::run(float* d_out, size_t d_out_cap) {
         launch_ln(xa, xb, nullptr, e.g2, e.b2, xa, H, 0, LX.map, st);
         R.count(0, 12.0 * LX.valid_rows * H);
     }
-    { Runner::Opt o; o.y0 = stats; o.ldy0 = 2 * I; R.conv(V.enc_proj, xa, H, LX, o); }
+    { Runner::Opt o; o.y0 = stats; o.ldy0 = 2 * I; o.tc_ok = true; R.conv(V.enc_proj, xa, H, LX, o); }
     R.end();
     if (debug) { dbg["x"] = {xa, H}; dbg_level["x"] = 0; dbg["stats"] = {stats, 2 * I}; dbg_level["stats"] = 0; }
 
