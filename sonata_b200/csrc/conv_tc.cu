@@ -14,10 +14,10 @@
 // have N = C_out = 32..128.
 //
 // Data path (no tensor maps needed):
-//   * activations: producer warps read the (128 + span)-row WINDOW of a K-block from HBM with coalesced
-//     128-bit loads (the whole stage in flight before first use), apply the leaky-ReLU prologue, split
-//     hi/lo and store ONE image row per time step:  [hi: 32 ch bf16 | lo: 32 ch bf16] = 128 B, in the
-//     canonical K-major SWIZZLE_128B layout (row r at r*128 B, 16-B chunk c at (c ^ (r & 7))).  A tap is
+//   * activations: producer warps cp.async (LDGSTS) the raw (128 + span)-row WINDOW of a K-block from HBM
+//     straight into the smem ring, several stages ahead, then apply the leaky-ReLU prologue, split hi/lo
+//     and rewrite each 128-byte row IN PLACE as  [hi: 32 ch bf16 | lo: 32 ch bf16]  in the canonical
+//     K-major SWIZZLE_128B layout (row r at r*128 B, 16-B chunk c at (c ^ (r & 7))).  A tap is
 //     only a descriptor whose start address is shifted by off_t rows (the swizzle is a function of the
 //     absolute smem address), so a k-tap conv stages its input once and issues k x 6 MMAs on it;
 //   * weights: pre-split, pre-swizzled [hi|lo] tile images written at voice-load time; one
@@ -27,9 +27,9 @@
 //   * epilogue: tcgen05.ld 32x32b.x32 (LDTM) -> bias / gate / residual / scale / accumulate -> HBM, with
 //     the residual / read-modify-write operands prefetched before the accumulator is awaited.
 // Persistent CTAs (one per SM) walk tiles blockIdx.x, +gridDim.x, ...; three mbarrier pipelines
-// (activation ring, weight ring, double-buffered TMEM accumulator) run across tile boundaries.
-// Warps: w0 MMA issuer (+TMEM alloc), w1 weight producer, w2-5 / w6-9 two activation-producer groups
-// (alternating stages), w10-13 epilogue.  Every mbarrier wait carries a watchdog that traps instead of
+// (activation ring, weight ring, 4-stage TMEM accumulator ring) run across tile boundaries.
+// Warps: w0/w1 MMA issuers on alternating tiles (w0 also allocates TMEM), w2 weight producer, w4-7 / w8-11
+// two activation-producer groups, w12-15 / w16-19 two epilogue groups (one per half-pipeline).  Every mbarrier wait carries a watchdog that traps instead of
 // hanging the GPU.
 #include "common.cuh"
 #include <cuda_bf16.h>
@@ -125,48 +125,56 @@ __device__ __forceinline__ uint32_t split2(float a, float b, uint32_t& lo) {
 }
 
 struct TcLaunch {
-    int nt;          // columns per CTA tile (multiple of 32, <= 256)
+    int nt;          // columns per CTA tile (multiple of 32, <= 128)
     int win;         // window rows (multiple of 8)
-    int na;          // activation ring stages
-    int ws;          // weight ring stages (or all (K-block, tap) stages when resident)
+    int na;          // activation ring stages PER PIPELINE
+    int ws;          // weight stages: all (K-block, tap) stages when resident (shared), else ring stages PER PIPELINE
     int resident;    // weights loaded once per CTA (single n-tile, short K loop)
-    int tmem_cols;   // power of two >= 2*nt (two accumulator stages)
+    int tmem_cols;   // power of two >= 4*nt (two accumulator stages per pipeline)
     int ntiles_m, ntiles_n;
     uint32_t idesc;
 };
 
 constexpr int TC_MAXCH = 7;             // 32-B input pieces per producer thread per stage (win <= 224 rows)
 constexpr int TC_GROUP = 128;           // threads per producer group
-constexpr int TC_EPI0 = 10;             // first epilogue warp
-constexpr int TC2_THREADS = 448;        // w0 MMA, w1 weights, w2-5 / w6-9 activation groups, w10-13 epilogue
-constexpr int TC_MAX_ASTAGES = 6;
-constexpr int TC_MAX_WRING = 44;        // barrier slots for the weight ring / resident set
+constexpr int TC_PROD0 = 4;             // first activation-producer warp
+constexpr int TC_EPI0 = 12;             // first epilogue warp
+constexpr int TC2_THREADS = 640;        // w0/w1 MMA issuers, w2/w3 weight producers, w4-7 / w8-11 activation groups,
+                                        // w12-15 / w16-19 epilogue groups (pipeline 0 / 1)
+constexpr int TC_MAX_ASTAGES = 4;       // per pipeline
+constexpr int TC_MAX_WRING = 44;        // barrier slots for the resident weight set (or 2 x ring)
 
+// The CTA runs TWO independent half-pipelines (p = 0 / 1 own tiles tl = p, p+2, ...): one thread can issue an
+// M=128 MMA only every ~83 cycles whatever N is, while two issuing warps double the aggregate rate
+// (tools/micro/mma_bench.cu: N=32 385 -> 774 MAC/clk/SM, N=128 1572 -> 2046 = peak).  Each pipeline has its
+// own activation ring, weight ring and accumulator pair, so no mbarrier can be lapped by the other pipeline.
 __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs a, const TcLaunch L) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t a_buf = (uint32_t)L.win * 128u;              // one [hi|lo] window image
     const uint32_t w_stage = (uint32_t)L.nt * 128u;             // one [hi|lo] weight tile image
-    uint8_t* A0 = smem;
-    uint8_t* W0 = A0 + (size_t)L.na * a_buf;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(W0 + (size_t)L.ws * w_stage);
+    const int wslots = L.resident ? L.ws : 2 * L.ws;
+    uint8_t* A0 = smem;                                         // [2][na] stages
+    uint8_t* W0 = A0 + (size_t)2 * L.na * a_buf;                // resident: [ws]; ring: [2][ws]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(W0 + (size_t)wslots * w_stage);
     uint64_t* w_full = bars;                               // [TC_MAX_WRING]
     uint64_t* w_empty = w_full + TC_MAX_WRING;             // [TC_MAX_WRING]
-    uint64_t* a_full = w_empty + TC_MAX_WRING;             // [TC_MAX_ASTAGES]
-    uint64_t* a_empty = a_full + TC_MAX_ASTAGES;           // [TC_MAX_ASTAGES]
-    uint64_t* acc_full = a_empty + TC_MAX_ASTAGES;         // [2]
-    uint64_t* acc_empty = acc_full + 2;                    // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* a_full = w_empty + TC_MAX_WRING;             // [2][TC_MAX_ASTAGES]
+    uint64_t* a_empty = a_full + 2 * TC_MAX_ASTAGES;       // [2][TC_MAX_ASTAGES]
+    uint64_t* acc_full = a_empty + 2 * TC_MAX_ASTAGES;     // [4]  (index = pipeline + 2 * stage)
+    uint64_t* acc_empty = acc_full + 4;                    // [4]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 4);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nkb = a.cin / 32;
+    const int per_tile = nkb * a.ntaps;
     const int total_tiles = L.ntiles_m * L.ntiles_n;
     const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (tid == 0) {
-        for (int s = 0; s < L.ws; s++) { mbar_init(smem_u32(&w_full[s]), 1); mbar_init(smem_u32(&w_empty[s]), 1); }
-        for (int s = 0; s < L.na; s++) { mbar_init(smem_u32(&a_full[s]), TC_GROUP); mbar_init(smem_u32(&a_empty[s]), 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(smem_u32(&acc_full[s]), 1); mbar_init(smem_u32(&acc_empty[s]), 128); }
+        for (int s = 0; s < wslots; s++) { mbar_init(smem_u32(&w_full[s]), 1); mbar_init(smem_u32(&w_empty[s]), 1); }
+        for (int s = 0; s < 2 * TC_MAX_ASTAGES; s++) { mbar_init(smem_u32(&a_full[s]), TC_GROUP); mbar_init(smem_u32(&a_empty[s]), 1); }
+        for (int s = 0; s < 4; s++) { mbar_init(smem_u32(&acc_full[s]), 1); mbar_init(smem_u32(&acc_empty[s]), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -179,32 +187,42 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        // ===================== MMA issuer =====================
+    if (warp < 2) {
+        // ===================== MMA issuer of pipeline p = warp =====================
         // The WHOLE warp walks the loop with warp-uniform values (descriptors live in uniform registers, no
         // R2UR waterfall loops); only the tcgen05 instructions sit under elect.sync.
         // K-major SWIZZLE_128B descriptor (cute::UMMA::SmemDescriptor v1): start>>4 | LBO 1<<16 | SBO (1024>>4)<<32 |
         // version 1<<46 | layout SWIZZLE_128B 2<<61; "matrix base offset" stays 0 even for row-shifted starts
         // (measured: a non-zero base offset breaks every k > 1 case).
+        const int p = warp;
         const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-        int it = 0, wit = 0;
-        for (int tl = 0; tl < my_tiles; tl++) {
-            const int acc = tl & 1;
-            mbar_wait(smem_u32(&acc_empty[acc]), (uint32_t)(((tl >> 1) & 1) ^ 1));
+        uint8_t* Ap = A0 + (size_t)p * L.na * a_buf;
+        uint8_t* Wp = L.resident ? W0 : W0 + (size_t)p * L.ws * w_stage;
+        uint64_t* wf = L.resident ? w_full : w_full + p * L.ws;
+        uint64_t* we = L.resident ? w_empty : w_empty + p * L.ws;
+        int lit = 0, lwit = 0;                 // pipeline-local stage / weight-stage counters
+        for (int tl = p, lt = 0; tl < my_tiles; tl += 2, lt++) {
+            const int accs = lt & 1;           // accumulator stage within the pipeline
+            const int acc = p + 2 * accs;
+            mbar_wait(smem_u32(&acc_empty[acc]), (uint32_t)(((lt >> 1) & 1) ^ 1));
             tc_fence_after();
             const uint32_t dcol = tmem_base + (uint32_t)(acc * L.nt);
-            for (int kb = 0; kb < nkb; kb++, it++) {
-                const int as = it % L.na;
-                mbar_wait(smem_u32(&a_full[as]), (uint32_t)((it / L.na) & 1));
+            for (int kb = 0; kb < nkb; kb++, lit++) {
+                const int as = lit % L.na;
+                mbar_wait(smem_u32(&a_full[p * TC_MAX_ASTAGES + as]), (uint32_t)((lit / L.na) & 1));
                 tc_fence_after();
-                const uint32_t aimg = smem_u32(A0 + (size_t)as * a_buf) >> 4;
-                for (int t = 0; t < a.ntaps; t++, wit++) {
-                    int ws; uint32_t wpar;
-                    if (L.resident) { ws = kb * a.ntaps + t; wpar = 0; }
-                    else { ws = wit % L.ws; wpar = (uint32_t)((wit / L.ws) & 1); }
-                    mbar_wait(smem_u32(&w_full[ws]), wpar);
-                    tc_fence_after();
-                    const uint32_t wimg = smem_u32(W0 + (size_t)ws * w_stage) >> 4;
+                const uint32_t aimg = smem_u32(Ap + (size_t)as * a_buf) >> 4;
+                for (int t = 0; t < a.ntaps; t++, lwit++) {
+                    int ws;
+                    if (L.resident) {
+                        ws = kb * a.ntaps + t;
+                        if (lt == 0) { mbar_wait(smem_u32(&wf[ws]), 0); tc_fence_after(); }   // loaded once, stays
+                    } else {
+                        ws = lwit % L.ws;
+                        mbar_wait(smem_u32(&wf[ws]), (uint32_t)((lwit / L.ws) & 1));
+                        tc_fence_after();
+                    }
+                    const uint32_t wimg = smem_u32(Wp + (size_t)ws * w_stage) >> 4;
                     const uint32_t arow = aimg + (uint32_t)(a.tap_off[t] - a.min_off) * 8u;      // rows * 128 B >> 4
                     if (elect_one()) {
 #pragma unroll
@@ -217,79 +235,107 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                             tc_mma_bf16(dcol, dal, dwh, L.idesc, 1u);
                             tc_mma_bf16(dcol, dah, dwl, L.idesc, 1u);
                         }
-                        if (!L.resident) tc_commit(smem_u32(&w_empty[ws]));   // slot reusable once these MMAs retire
+                        if (!L.resident) tc_commit(smem_u32(&we[ws]));   // slot reusable once these MMAs retire
                     }
                     __syncwarp();
                 }
-                if (elect_one()) tc_commit(smem_u32(&a_empty[as]));
+                if (elect_one()) tc_commit(smem_u32(&a_empty[p * TC_MAX_ASTAGES + as]));
                 __syncwarp();
             }
             if (elect_one()) tc_commit(smem_u32(&acc_full[acc]));
             __syncwarp();
         }
-    } else if (warp == 1) {
-        // ===================== weight producer =====================
+    } else if (warp < 4) {
+        // ===================== weight producer of pipeline p = warp - 2 =====================
+        const int p = warp - 2;
         if (lane == 0) {
-            const int per_tile = nkb * a.ntaps;
             if (L.resident) {
-                const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wtc);
-                for (int s = 0; s < per_tile; s++) {
-                    mbar_expect_tx(smem_u32(&w_full[s]), w_stage);
-                    bulk_g2s(smem_u32(W0 + (size_t)s * w_stage), wsrc + (size_t)s * w_stage, w_stage, smem_u32(&w_full[s]));
+                if (p == 0) {
+                    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wtc);
+                    for (int s = 0; s < per_tile; s++) {
+                        mbar_expect_tx(smem_u32(&w_full[s]), w_stage);
+                        bulk_g2s(smem_u32(W0 + (size_t)s * w_stage), wsrc + (size_t)s * w_stage, w_stage, smem_u32(&w_full[s]));
+                    }
                 }
             } else {
-                int wit = 0;
-                for (int tl = 0; tl < my_tiles; tl++) {
+                uint8_t* Wp = W0 + (size_t)p * L.ws * w_stage;
+                uint64_t* wf = w_full + p * L.ws;
+                uint64_t* we = w_empty + p * L.ws;
+                int lwit = 0;
+                for (int tl = p; tl < my_tiles; tl += 2) {
                     const int tg = (int)blockIdx.x + tl * (int)gridDim.x;
                     const int n_tile = tg % L.ntiles_n;
                     const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wtc) + (size_t)n_tile * per_tile * w_stage;
-                    for (int i = 0; i < per_tile; i++, wit++) {
-                        const int ws = wit % L.ws;
-                        mbar_wait(smem_u32(&w_empty[ws]), (uint32_t)(((wit / L.ws) & 1) ^ 1));
-                        mbar_expect_tx(smem_u32(&w_full[ws]), w_stage);
-                        bulk_g2s(smem_u32(W0 + (size_t)ws * w_stage), wsrc + (size_t)i * w_stage, w_stage, smem_u32(&w_full[ws]));
+                    for (int i = 0; i < per_tile; i++, lwit++) {
+                        const int ws = lwit % L.ws;
+                        mbar_wait(smem_u32(&we[ws]), (uint32_t)(((lwit / L.ws) & 1) ^ 1));
+                        mbar_expect_tx(smem_u32(&wf[ws]), w_stage);
+                        bulk_g2s(smem_u32(Wp + (size_t)ws * w_stage), wsrc + (size_t)i * w_stage, w_stage, smem_u32(&wf[ws]));
                     }
                 }
             }
         }
         __syncwarp();
     } else if (warp < TC_EPI0) {
-        // ===================== activation producers: two groups of 128 threads, alternating stages ==========
-        const int grp = (warp - 2) >> 2;
-        const int gt = tid - 64 - grp * TC_GROUP;
+        // ===================== activation producers: group p feeds pipeline p =====================
+        // Raw fp32 rows (32 ch = 128 B) are cp.async'ed (LDGSTS, zero-fill outside the array) straight into the
+        // ring, na-1 stages ahead, and converted IN PLACE to the [hi|lo] bf16 image of the same 128 bytes: the
+        // four lanes that share a row read their 32-B pieces, __syncwarp(), then overwrite the row.
+        const int p = (warp - TC_PROD0) >> 2;
+        const int gt = tid - TC_PROD0 * 32 - p * TC_GROUP;
         const int npiece = L.win * 4;                  // 32-B pieces (8 channels) per stage
         const float slope = a.in_slope;
-        int it = 0;
-        for (int tl = 0; tl < my_tiles; tl++) {
-            const int tg = (int)blockIdx.x + tl * (int)gridDim.x;
-            const int q0 = (tg / L.ntiles_n) * 128;
-            const int rbase = q0 + a.min_off;
-            for (int kb = 0; kb < nkb; kb++, it++) {
-                if ((it & 1) != grp) continue;
-                const int as = it % L.na;
-                const float* xk = a.x + kb * 32;
-                float4 v[TC_MAXCH][2];
+        uint8_t* Ap = A0 + (size_t)p * L.na * a_buf;
+        const int nloc = (my_tiles - p + 1) / 2;       // tiles owned by this pipeline
+        const int nst = nloc * nkb;                    // stages to produce
+        const int depth = L.na - 1;                    // stages in flight
+        auto issue_stage = [&](int j) {
+            const int lt = j / nkb, kb = j - lt * nkb;
+            const int tg = (int)blockIdx.x + (p + 2 * lt) * (int)gridDim.x;
+            const int rbase = (tg / L.ntiles_n) * 128 + a.min_off;
+            const int as = j % L.na;
+            mbar_wait(smem_u32(&a_empty[p * TC_MAX_ASTAGES + as]), (uint32_t)(((j / L.na) & 1) ^ 1));
+            const uint32_t img = smem_u32(Ap + (size_t)as * a_buf);
+            const float* xk = a.x + kb * 32;
 #pragma unroll
-                for (int u = 0; u < TC_MAXCH; u++) {          // the whole stage in flight before the first use
-                    const int idx = gt + u * TC_GROUP;
-                    v[u][0] = v[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (idx < npiece) {
-                        const int gr = rbase + (idx >> 2);
-                        if (gr >= 0 && gr < a.rows_in) {
-                            const float4* src = reinterpret_cast<const float4*>(xk + (size_t)gr * a.ldx + (idx & 3) * 8);
-                            v[u][0] = src[0];
-                            v[u][1] = src[1];
-                        }
-                    }
+            for (int u = 0; u < TC_MAXCH; u++) {
+                const int idx = gt + u * TC_GROUP;
+                if (idx < npiece) {
+                    const int gr = rbase + (idx >> 2);
+                    const bool ok = gr >= 0 && gr < a.rows_in;
+                    const float* src = ok ? xk + (size_t)gr * a.ldx + (idx & 3) * 8 : a.x;
+                    const uint32_t dst = img + (uint32_t)idx * 32u;
+                    const uint32_t nbytes = ok ? 16u : 0u;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 16u), "l"(src + 4), "r"(nbytes) : "memory");
                 }
-                mbar_wait(smem_u32(&a_empty[as]), (uint32_t)(((it / L.na) & 1) ^ 1));
-                uint8_t* img = A0 + (size_t)as * a_buf;
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        int ji = 0;
+        for (; ji < depth && ji < nst; ji++) issue_stage(ji);
+        for (int j = 0; j < nst; j++) {
+            const int pending = ji - 1 - j;            // younger groups allowed to stay in flight
+            if (pending >= 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
+            else if (pending == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+            else if (pending == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            const int as = j % L.na;
+            uint8_t* img = Ap + (size_t)as * a_buf;
 #pragma unroll
-                for (int u = 0; u < TC_MAXCH; u++) {
-                    const int idx = gt + u * TC_GROUP;
-                    if (idx >= npiece) continue;
+            for (int u = 0; u < TC_MAXCH; u++) {
+                const int idx = gt + u * TC_GROUP;
+                const bool live = idx < npiece;        // warp-uniform per u except in the last partial warp
+                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                if (live) {
+                    v0 = *reinterpret_cast<const float4*>(img + (size_t)idx * 32);
+                    v1 = *reinterpret_cast<const float4*>(img + (size_t)idx * 32 + 16);
+                }
+                __syncwarp();                          // every lane of the row has read before anyone overwrites
+                if (live) {
                     const int r = idx >> 2, c = idx & 3;
-                    float e[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
+                    float e[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
                     for (int i = 0; i < 8; i++) e[i] = e[i] > 0.f ? e[i] : e[i] * slope;
                     uint4 hi, lo;
@@ -302,55 +348,59 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                     *reinterpret_cast<uint4*>(img + rowb + (((uint32_t)c ^ sw) << 4)) = hi;
                     *reinterpret_cast<uint4*>(img + rowb + (((uint32_t)(c + 4) ^ sw) << 4)) = lo;
                 }
-                fence_async_smem();                       // generic-proxy stores -> visible to the tensor core
-                mbar_arrive(smem_u32(&a_full[as]));
             }
+            fence_async_smem();                       // generic-proxy stores -> visible to the tensor core
+            mbar_arrive(smem_u32(&a_full[p * TC_MAX_ASTAGES + as]));
+            if (ji < nst) { issue_stage(ji); ji++; }
         }
     } else {
-        // ===================== epilogue (warps 10..13, one TMEM lane quadrant each) =====================
-        // Residual / read-modify-write operands of chunk 0 are prefetched BEFORE the accumulator is awaited.
+        // ===================== epilogue: warps 12-15 serve pipeline 0, warps 16-19 pipeline 1 =====================
+        // (one TMEM lane quadrant per warp).  The residual and the read-modify-write operand of chunk 0 are
+        // folded into one addend  m = res*scale + prev  and prefetched BEFORE the accumulator is awaited.
+        const int p = (warp - TC_EPI0) >> 2;
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
         const int nch = L.nt / 32;
         const bool gate = a.act == ACT_GATE;
-        for (int tl = 0; tl < my_tiles; tl++) {
+        for (int tl = p, lt = 0; tl < my_tiles; tl += 2, lt++) {
             const int tg = (int)blockIdx.x + tl * (int)gridDim.x;
             const int q = (tg / L.ntiles_n) * 128 + row;
             const int n0 = (tg % L.ntiles_n) * L.nt;
-            const int acc = tl & 1;
+            const int acc = p + 2 * (lt & 1);
             const bool inrange = q < a.rows_q;
             const bool valid = inrange && row_valid(a.map, q);
             const size_t orow = (size_t)q * a.orow_mul + a.orow_add;
-            float rn[32], pn[32];
+            float m[32];
             auto prefetch = [&](int ch) {
                 const int n = n0 + ch * 32;
                 const bool live = valid && n < a.cout && !gate;
-                if (a.res) {
+                const bool lo_side = n < a.split;
+                const bool accum = lo_side ? a.acc0 : a.acc1;
+#pragma unroll
+                for (int j = 0; j < 32; j++) m[j] = 0.f;
+                if (a.res && live) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (live) r = *reinterpret_cast<const float4*>(a.res + orow * a.ldres + n + j);
-                        rn[j] = r.x; rn[j + 1] = r.y; rn[j + 2] = r.z; rn[j + 3] = r.w;
+                        const float4 r = *reinterpret_cast<const float4*>(a.res + orow * a.ldres + n + j);
+                        m[j] = r.x * a.scale; m[j + 1] = r.y * a.scale; m[j + 2] = r.z * a.scale; m[j + 3] = r.w * a.scale;
                     }
                 }
-                const bool lo_side = n < a.split;
-                if (lo_side ? a.acc0 : a.acc1) {
+                if (accum && live) {
                     const float* src = lo_side ? a.y0 + orow * a.ldy0 + n : a.y1 + orow * a.ldy1 + (n - a.split);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (live) r = *reinterpret_cast<const float4*>(src + j);
-                        pn[j] = r.x; pn[j + 1] = r.y; pn[j + 2] = r.z; pn[j + 3] = r.w;
+                        const float4 r = *reinterpret_cast<const float4*>(src + j);
+                        m[j] += r.x; m[j + 1] += r.y; m[j + 2] += r.z; m[j + 3] += r.w;
                     }
                 }
             };
             prefetch(0);
-            mbar_wait(smem_u32(&acc_full[acc]), (uint32_t)((tl >> 1) & 1));
+            mbar_wait(smem_u32(&acc_full[acc]), (uint32_t)((lt >> 1) & 1));
             tc_fence_after();
             for (int ch = 0; ch < nch; ch++) {
                 float o[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * L.nt + ch * 32), o);
-                if (ch == nch - 1) {          // accumulator fully read: hand it back to the MMA warp
+                if (ch == nch - 1) {          // accumulator fully read: hand it back to its MMA warp
                     tc_fence_before();
                     mbar_arrive(smem_u32(&acc_empty[acc]));
                 }
@@ -382,21 +432,10 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
 #pragma unroll
                     for (int j = 0; j < 32; j++) o[j] = fmaxf(o[j], 0.f);
                 }
-                if (a.res && valid) {
+                if (accum && !valid) continue;     // accumulated buffers keep their zeros in gap rows
 #pragma unroll
-                    for (int j = 0; j < 32; j++) o[j] += rn[j];
-                }
-#pragma unroll
-                for (int j = 0; j < 32; j++) o[j] *= a.scale;
+                for (int j = 0; j < 32; j++) o[j] = valid ? fmaf(o[j], a.scale, m[j]) : 0.f;
                 float* dst = lo_side ? a.y0 + orow * a.ldy0 + n : a.y1 + orow * a.ldy1 + (n - a.split);
-                if (accum) {
-                    if (!valid) continue;
-#pragma unroll
-                    for (int j = 0; j < 32; j++) o[j] += pn[j];
-                } else if (!valid) {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) o[j] = 0.f;
-                }
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
@@ -412,13 +451,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
 }
 
 bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem) {
-    if (!a.wtc || a.tc_nt <= 0) return false;
+    if (!a.wtc || a.tc_nt <= 0 || a.tc_nt > 128) return false;
     L.nt = a.tc_nt;
     L.win = (128 + a.span + 7) & ~7;
     if (L.win * 4 > TC_MAXCH * TC_GROUP) return false;
     L.tmem_cols = 32;
-    while (L.tmem_cols < 2 * L.nt) L.tmem_cols <<= 1;
-    if (L.tmem_cols > 512) return false;
+    while (L.tmem_cols < 4 * L.nt) L.tmem_cols <<= 1;
     // kind::f16 instruction descriptor: D fp32 (1<<4), A = B = BF16 (1<<7, 1<<10), K-major both, N>>3, M>>4
     L.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(L.nt >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     L.ntiles_m = (a.rows_q + 127) / 128;
@@ -427,11 +465,11 @@ bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem) {
     const size_t w_stage = (size_t)L.nt * 128;
     const int per_tile = (a.cin / 32) * a.ntaps;
     const size_t budget = 225 * 1024 - 2048;
-    const size_t bar_bytes = (2 * TC_MAX_WRING + 2 * TC_MAX_ASTAGES + 4) * 8 + 16;
-    L.resident = (L.ntiles_n == 1 && per_tile <= TC_MAX_WRING && per_tile * w_stage + 3 * a_buf + bar_bytes <= budget) ? 1 : 0;
-    L.ws = L.resident ? per_tile : (per_tile < 6 ? per_tile : 6);
+    const size_t bar_bytes = (2 * TC_MAX_WRING + 4 * TC_MAX_ASTAGES + 8) * 8 + 16;
+    L.resident = (L.ntiles_n == 1 && per_tile <= TC_MAX_WRING && per_tile * w_stage + 4 * a_buf + bar_bytes <= budget) ? 1 : 0;
+    L.ws = L.resident ? per_tile : (per_tile < 4 ? per_tile : 4);
     if (!L.resident && L.ws < 2) L.ws = 2;
-    auto total = [&]() { return (size_t)L.na * a_buf + (size_t)L.ws * w_stage + bar_bytes; };
+    auto total = [&]() { return (size_t)2 * L.na * a_buf + (size_t)(L.resident ? L.ws : 2 * L.ws) * w_stage + bar_bytes; };
     L.na = TC_MAX_ASTAGES;
     while (L.na > 2 && total() > budget) L.na--;
     while (!L.resident && L.ws > 2 && total() > budget) L.ws--;

@@ -65,6 +65,12 @@ CASES = [
     (256, 192, 576, 1, 1, 1.0, 0, False, 1.0, False, None),
     (256, 768, 192, 3, 1, 1.0, 0, False, 1.0, False, None),
     (256, 192, 768, 3, 1, 1.0, 1, False, 1.0, False, None),
+    # persistent multi-tile paths: several tiles per CTA on both half-pipelines (resident and ring weights)
+    (148 * 128 * 3 + 384, 32, 32, 3, 2, 0.1, 0, True, 1.0, False, 148 * 128 * 3 + 300),
+    (148 * 128 * 5, 64, 64, 7, 12, 0.1, 0, True, 1 / 3, True, None),
+    (20480, 192, 384, 5, 1, 1.0, 2, False, 1.0, False, 20000),
+    (20480 + 128, 192, 384, 1, 1, 1.0, 0, False, 1.0, True, None),
+    (9 * 148 * 128 // 4, 128, 128, 3, 2, 0.1, 0, True, 1.0, False, None),
 ]
 
 if __name__ == "__main__":
