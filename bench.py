@@ -126,7 +126,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3"])
-    ap.add_argument("--backend", type=int, default=int(os.environ.get("SB200_BACKEND", "0")))
+    ap.add_argument("--backend", type=int, default=int(os.environ.get("SB200_BACKEND", "1")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -311,7 +311,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * wall_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg_desc,
             "device_ms_per_step": dev_ms_max / args.steps, "audio_s_per_step": audio_total / args.steps,
-            "backend": "tcgen05-3xTF32" if args.backend == 1 else "fp32-simt",
+            "backend": "tcgen05-bf16x2 (flow+decoder), fp32 CUDA cores (encoder, duration predictor)" if args.backend == 1 else "fp32-simt",
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(8 * ids_per_step),
                     "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps},

@@ -115,13 +115,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-// pack (hi, lo) halves of two consecutive channels: returns the hi pair, writes the lo pair
+// pack (hi, lo) halves of two consecutive channels with the packed converter (one cvt.rn.bf16x2.f32 per
+// pair instead of two scalar converts): returns the hi pair, writes the lo pair
 __device__ __forceinline__ uint32_t split2(float a, float b, uint32_t& lo) {
-    const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
-    const __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha));
-    const __nv_bfloat16 lb = __float2bfloat16_rn(b - __bfloat162float(hb));
-    lo = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
-    return (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+    const float ha = __uint_as_float(hb << 16), hbf = __uint_as_float(hb & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hbf);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+    return hb;
 }
 
 struct TcLaunch {
@@ -369,11 +371,15 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
             const int acc = p + 2 * (lt & 1);
             const bool inrange = q < a.rows_q;
             const bool valid = inrange && row_valid(a.map, q);
-            const size_t orow = (size_t)q * a.orow_mul + a.orow_add;
+            const size_t orow0 = (size_t)q * a.orow_mul + a.orow_add;
             float m[32];
+            // phase-fused ConvTranspose (phase_cols > 0): column block n / phase_cols is the output phase,
+            // i.e. output row q*u + phase and column n % phase_cols
             auto prefetch = [&](int ch) {
-                const int n = n0 + ch * 32;
+                int n = n0 + ch * 32;
                 const bool live = valid && n < a.cout && !gate;
+                size_t orow = orow0;
+                if (a.phase_cols) { orow += (size_t)(n / a.phase_cols); n %= a.phase_cols; }
                 const bool lo_side = n < a.split;
                 const bool accum = lo_side ? a.acc0 : a.acc1;
 #pragma unroll
@@ -404,15 +410,18 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                     tc_fence_before();
                     mbar_arrive(smem_u32(&acc_empty[acc]));
                 }
-                const int n = n0 + ch * 32;
-                const bool lo_side = n < a.split;
-                const int accum = lo_side ? a.acc0 : a.acc1;
+                int n = n0 + ch * 32;
                 if (ch > 0) prefetch(ch);
                 if (!inrange || n >= a.cout) continue;
+                const int nb = n;                       // bias / weight column
+                size_t orow = orow0;
+                if (a.phase_cols) { orow += (size_t)(n / a.phase_cols); n %= a.phase_cols; }
+                const bool lo_side = n < a.split;
+                const int accum = lo_side ? a.acc0 : a.acc1;
                 if (a.bias) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        const float4 b = *reinterpret_cast<const float4*>(a.bias + n + j);
+                        const float4 b = *reinterpret_cast<const float4*>(a.bias + nb + j);
                         o[j] += b.x; o[j + 1] += b.y; o[j + 2] += b.z; o[j + 3] += b.w;
                     }
                 }

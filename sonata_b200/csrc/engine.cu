@@ -220,7 +220,26 @@ void run_decoder(Runner& R, const Level& LY, const float* s, float* d_wav, const
             tmp[0] = pool[3]; tmp[1] = ntmp > 2 ? pool[4] : nullptr; tmp[2] = ntmp > 2 ? pool[5] : nullptr;
         }
         R.begin("dec.up" + std::to_string(i));
-        for (int p = 0; p < st.u; p++) {
+        bool fused_done = false;
+        if (v.backend == 1 && st.fused.wtc) {
+            // tcgen05 path: all u phases in one launch (input read once, N = u*cout columns)
+            ConvArgs pa{};
+            pa.x = cur; pa.ldx = st.cin; pa.rows_in = Lin.map.rows; pa.cin = st.cin; pa.in_slope = 0.1f;
+            pa.w = nullptr; pa.bias = st.fused.bias; pa.ldw = st.fused.ldw; pa.cout = st.fused.cout;
+            pa.wtc = st.fused.wtc; pa.tc_nt = st.fused.tc_nt;
+            pa.ntaps = st.fused.ntaps; memcpy(pa.tap_off, st.fused.tap_off, sizeof(pa.tap_off));
+            pa.min_off = st.fused.min_off; pa.span = st.fused.span;
+            pa.rows_q = Lin.map.rows; pa.orow_mul = st.u; pa.orow_add = 0; pa.phase_cols = st.cout;
+            pa.map = Lin.map; pa.act = ACT_NONE; pa.scale = 1.f;
+            pa.y0 = up; pa.ldy0 = st.cout; pa.split = st.fused.cout; pa.y1 = up; pa.ldy1 = st.cout;
+            if (conv_tc_supported(pa)) {
+                launch_conv_tc(pa, R.st);
+                const double vr = (double)Lin.valid_rows;
+                R.count(2.0 * vr * st.cin * st.cout * st.k, 4.0 * (vr * (st.cin + (double)st.u * st.cout) + (double)st.cin * st.cout * st.k));
+                fused_done = true;
+            }
+        }
+        for (int p = 0; p < st.u && !fused_done; p++) {
             Runner::Opt o; o.in_slope = 0.1f; o.y0 = up; o.ldy0 = st.cout; o.orow_mul = st.u; o.orow_add = p; o.tc_ok = true;
             R.conv(st.phase[p], cur, st.cin, Lin, o);
         }

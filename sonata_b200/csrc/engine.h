@@ -59,7 +59,7 @@ struct DDSW { float* wdw[3]; float* bdw[3]; ConvW c1x1[3]; float *g1[3], *b1[3],
 struct CFlowW { float* pre_w; float* pre_b; DDSW dds; ConvW proj; int ccol, tcol; };
 struct CouplingW { ConvW pre; std::vector<ConvW> in, rs; ConvW post; int cond_off, tgt_off; };
 struct ResBW { int k; std::vector<int> dils; std::vector<ConvW> c1, c2; };
-struct UpStageW { int u, k, cin, cout; std::vector<ConvW> phase; std::vector<ResBW> res; };
+struct UpStageW { int u, k, cin, cout; std::vector<ConvW> phase; ConvW fused; std::vector<ResBW> res; };   // fused: all phases as one N = u*cout conv (tcgen05 path)
 
 struct SynthConfig { long long speaker = 0; bool has_speaker = false; float noise_scale = 0.667f, length_scale = 1.f, noise_w = 0.8f; };
 
@@ -96,7 +96,7 @@ struct Voice {
     int c_last = 0;
     size_t weight_bytes = 0;
 
-    int backend = 0;                // 0 SIMT fp32, 1 tcgen05 3xTF32 (where implemented)
+    int backend = 1;                // 1 (default) tcgen05 bf16x2 for flow + decoder contractions, 0 = fp32 CUDA cores everywhere
     unsigned long long noise_seed = 0x5eed5eedULL;
     std::mutex pool_mu;
     std::vector<Context*> pool;

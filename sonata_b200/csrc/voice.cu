@@ -4,6 +4,7 @@
 // session initialisation (pre-packing) does on the reference side.
 #include "engine.h"
 #include "json.hpp"
+#include <algorithm>
 #include <cstring>
 #include <fstream>
 #include <sstream>
@@ -408,6 +409,32 @@ Voice* load_voice(const std::string& config_path, int device) {
                 c.w = U.up(wt); c.bias = U.up(bt);
                 add_tc_images(U, c, wt);
                 st.phase.push_back(c);
+            }
+            {
+                // all phases as ONE conv: taps = union of the phase taps, column p*cout + co = phase p, channel co
+                std::vector<int> offs;
+                for (auto& ph : st.phase) for (int t = 0; t < ph.ntaps; t++)
+                    if (std::find(offs.begin(), offs.end(), ph.tap_off[t]) == offs.end()) offs.push_back(ph.tap_off[t]);
+                std::sort(offs.begin(), offs.end());
+                ConvW f;
+                f.cin = st.cin; f.cout = st.u * st.cout; f.ntaps = (int)offs.size(); f.ldw = f.cout;
+                f.min_off = offs.front(); f.span = offs.back() - offs.front();
+                std::vector<float> wt((size_t)f.ntaps * f.cin * f.ldw, 0.f), bt(f.ldw, 0.f);
+                for (int p = 0; p < st.u; p++) {
+                    const int pp = p + pad;
+                    for (int t = 0; t < f.ntaps; t++) {
+                        f.tap_off[t] = offs[t];
+                        const int kk = -offs[t] * st.u + pp;       // tap offset = -d, kernel index = d*u + p + pad
+                        if (kk < 0 || kk >= st.k) continue;
+                        for (int ci = 0; ci < f.cin; ci++)
+                            for (int n = 0; n < st.cout; n++)
+                                wt[((size_t)t * f.cin + ci) * f.ldw + p * st.cout + n] = w.f[((size_t)ci * st.cout + n) * st.k + kk];
+                    }
+                    for (int n = 0; n < st.cout; n++) bt[p * st.cout + n] = b.f[n];
+                }
+                f.bias = U.up(bt);
+                if (f.ntaps <= SB_MAX_TAPS && st.cout % 32 == 0) add_tc_images(U, f, wt);
+                st.fused = f;
             }
             C /= 2;
             for (int j = 0; j < nk; j++) {
