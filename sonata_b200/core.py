@@ -78,6 +78,13 @@ class AudioSamples:
     def __init__(self, samples=()):
         self._v = np.asarray(samples, dtype=np.float32).reshape(-1).copy()
 
+    @classmethod
+    def _wrap(cls, array: np.ndarray) -> "AudioSamples":
+        """Adopt `array` without copying (used for the library's pinned result buffers)."""
+        self = cls.__new__(cls)
+        self._v = array
+        return self
+
     def as_slice(self) -> np.ndarray:
         return self._v
 
@@ -106,12 +113,17 @@ class AudioSamples:
     def merge(self, other: "AudioSamples") -> None:
         self._v = np.concatenate([self._v, other._v])
 
+    def _own(self) -> None:
+        if not self._v.flags.writeable or self._v.base is not None:
+            self._v = self._v.copy()
+
     def crossfade(self, fade_samples: int) -> None:
         """samples.rs:144-157: quarter-sine fade on both ends, f(i) = sin(i/(n-1) * pi/2)."""
         length = len(self)
         n = min(fade_samples, length // 2)
         if n <= 0:
             return
+        self._own()
         att = np.float32(n - 1)
         i = np.arange(n, dtype=np.float32)
         with np.errstate(divide="ignore", invalid="ignore"):

@@ -40,11 +40,31 @@ def _check(rc: int, err: N.sb200_error):
         raise SonataError.from_code(err.code if err.code else rc, msg)
 
 
+class _PinnedOwner:
+    """Keeps one library-owned (pinned) result buffer alive for as long as a numpy view of it exists."""
+
+    def __init__(self, a: N.sb200_audio):
+        self.a = N.sb200_audio(a.data, a.len, a.inference_ms, a.sample_rate)
+
+    def __del__(self):
+        try:
+            N.lib().sb200_audio_free(C.byref(self.a))
+        except Exception:
+            pass
+
+
 def _take_audio(a: N.sb200_audio) -> Audio:
-    arr = np.ctypeslib.as_array(a.data, shape=(a.len,)).copy() if a.len else np.zeros(0, np.float32)
-    out = Audio(AudioSamples(arr), int(a.sample_rate), float(a.inference_ms))
-    N.lib().sb200_audio_free(C.byref(a))
-    return out
+    """Zero-copy: the returned samples are a read-only view of the library's pinned host buffer (the
+    reference copies `outputs[0]` into a Vec at piper/src/lib.rs:392)."""
+    if not a.len:
+        N.lib().sb200_audio_free(C.byref(a))
+        return Audio(AudioSamples(np.zeros(0, np.float32)), int(a.sample_rate), float(a.inference_ms))
+    owner = _PinnedOwner(a)
+    buf = (C.c_float * a.len).from_address(C.addressof(a.data.contents))
+    buf._owner = owner
+    arr = np.frombuffer(buf, dtype=np.float32)
+    arr.flags.writeable = False
+    return Audio(AudioSamples._wrap(arr), int(a.sample_rate), float(a.inference_ms))
 
 
 class AdaptiveMelChunker:

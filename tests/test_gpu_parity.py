@@ -40,11 +40,13 @@ def _det(m):
     m.set_fallback_synthesis_config(PiperSynthesisConfig(None, 0.0, 1.0, 0.0))
 
 
+@pytest.mark.parametrize("backend", [1, 0], ids=["tcgen05", "fp32simt"])
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
-def test_cuda_matches_golden_vectors(path, models):
+def test_cuda_matches_golden_vectors(path, backend, models):
     g = np.load(path)
     q = os.path.basename(path).split("_")[0]
     m = models(q)
+    m.set_backend(backend)
     sc = g["scales"]
     m.set_fallback_synthesis_config(PiperSynthesisConfig(None, float(sc[0]), float(sc[1]), float(sc[2])))
     ew = [g["eps_w"]] if "eps_w" in g else None
@@ -58,13 +60,15 @@ def test_cuda_matches_golden_vectors(path, models):
     wav = job.fetch()[0].samples.as_slice()
     assert float(np.abs(wav - g["wav"]).max()) < TOL_WAV
     job.close()
+    m.set_backend(1)
 
 
+@pytest.mark.parametrize("backend", [1, 0], ids=["tcgen05", "fp32simt"])
 @pytest.mark.parametrize("quality,ns,noise", [("medium", (16, 40, 5, 0, 1), False), ("medium", (9, 21), True),
                                                ("high", (12, 3), False)])
-def test_every_stage_against_oracle(quality, ns, noise):
+def test_every_stage_against_oracle(quality, ns, noise, backend):
     from stage_report import stage_report
-    rep = stage_report(quality, ns, noise, backend=0, verbose=False)
+    rep = stage_report(quality, ns, noise, backend=backend, verbose=False)
     for u in rep["utts"]:
         assert u["durations_exact"] and u["y_len_ref"] == u["y_len_got"], u
         names = [s[0] for s in u["stages"]]
@@ -72,6 +76,18 @@ def test_every_stage_against_oracle(quality, ns, noise):
         for name, err, ref_max in u["stages"]:
             assert err != "SHAPE", (name, u)
             assert err < (TOL_WAV if name == "wav" else TOL_STAGE), (name, err, u["n_ids"])
+
+
+@pytest.mark.parametrize("backend", [1, 0], ids=["tcgen05", "fp32simt"])
+def test_conv_kernels_against_torch(backend, lib_built):
+    """Kernel-level unit check of both contraction backends (same ConvArgs contract): 1x1 / dilated k-tap,
+    leaky-ReLU prologue, gate / ReLU / residual / scale / accumulate epilogues, masked rows, and the
+    persistent multi-tile path of the tcgen05 kernel (several tiles per CTA on both half-pipelines)."""
+    from conv_unit import CASES, run_case
+    for c in CASES:
+        err, msg = run_case(backend, *c)
+        assert err is not None, (c, msg)
+        assert err < 1e-4, (c, err)
 
 
 def test_batched_equals_sequential(models):
@@ -142,6 +158,7 @@ def test_full_size_properties(models):
     assert float(np.abs(alone - auds[5].samples.as_slice()).max()) < 1e-5
     prof = {p["name"]: p for p in job.profile()}
     assert prof["dec.mrf2"]["launches"] == 6 and prof["dec.mrf2"]["ms"] > 0
+    assert prof["dec.up2"]["launches"] == 1          # phase-fused ConvTranspose on the tensor-core backend
     assert ms > 0
     job.close()
 
