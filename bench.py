@@ -73,6 +73,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """samples from here on belong to the timed region"""
+        self.first = len(self.lines)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -83,7 +87,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        first = getattr(self, "first", 0)
+        window = "timed region"
+        lines = self.lines[first:]
+        if not lines:                       # region shorter than one sampling period: use the warm-up samples too
+            lines, window = self.lines, "warm-up + timed region"
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -95,7 +104,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def tune_cpu_threads(quality: str, cores: int) -> int:
@@ -239,16 +248,17 @@ def main():
             frames, samples, _ = job.lengths()
         return sum(samples) / SR, ms, job
 
-    # warm-up
+    # warm-up (the clock sampler starts here so that nvidia-smi is already streaming when the timed region begins)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         _, _, j = step_device(all_batches)
         j.close()
 
-    sampler = ClockSampler(local_rank)
     prof_acc = {}
     barrier()
     launches0 = int(lib.sb200_launch_count())
-    sampler.start()
+    sampler.mark()
     t0 = time.perf_counter()
     audio_local, dev_ms = 0.0, 0.0
     for s in range(args.steps):
