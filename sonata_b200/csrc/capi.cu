@@ -322,10 +322,28 @@ int32_t sb200_debug_conv(int32_t device, int32_t backend, const float* x, int32_
         p.map = RowMap{dend, R, 1, R};
         p.act = act; p.scale = scale; p.res = dres; p.ldres = cout;
         p.y0 = dy; p.ldy0 = ycols; p.acc0 = accumulate; p.split = cout; p.y1 = dy; p.ldy1 = ycols; p.acc1 = accumulate;
+        long long* dtrace = nullptr;
+        const bool want_trace = backend == 1 && getenv("SB200_TC_TRACE") != nullptr;
+        if (want_trace) { SB_CUDA(cudaMalloc(&dtrace, 48 * 8 * 8)); SB_CUDA(cudaMemset(dtrace, 0, 48 * 8 * 8)); }
         if (backend == 1) {
             if (!conv_tc_supported(p)) throw Error(19, "conv shape not supported by the tcgen05 backend");
+            if (want_trace) launch_conv_tc(p, 0); // warm-up before the traced run (timing only: RMW cases run twice)
+            p.trace = dtrace;
             launch_conv_tc(p, 0);
         } else launch_conv_simt(p, 0);
+        if (want_trace) {
+            SB_CUDA(cudaDeviceSynchronize());
+            std::vector<long long> t(48 * 8);
+            SB_CUDA(cudaMemcpy(t.data(), dtrace, 48 * 8 * 8, cudaMemcpyDeviceToHost));
+            const long long t0 = t[0];
+            fprintf(stderr, "tile: prod_issue prod_landed prod_conv | mma_afull mma_issued | epi_accfull epi_tmem epi_stored  (cycles rel. to first issue)\n");
+            for (int i = 0; i < 48; i++) {
+                fprintf(stderr, "%3d:", i);
+                for (int k = 0; k < 8; k++) fprintf(stderr, " %9lld", t[i * 8 + k] ? t[i * 8 + k] - t0 : -1LL);
+                fprintf(stderr, "\n");
+            }
+            cudaFree(dtrace);
+        }
         cudaError_t e = cudaDeviceSynchronize();
         if (e == cudaSuccess) e = cudaMemcpy(y, dy, (size_t)rows * ycols * 4, cudaMemcpyDeviceToHost);
         cudaFree(dx); cudaFree(dy); cudaFree(dend); if (dres) cudaFree(dres);

@@ -44,6 +44,7 @@ struct ConvArgs {
     int ntaps; int tap_off[SB_MAX_TAPS]; int min_off; int span;   // span = max_off - min_off
     int rows_q; int orow_mul; int orow_add;
     int phase_cols;                                               // >0: fused polyphase ConvTranspose (tcgen05 path only)
+    long long* trace;                                             // optional per-role clock64() timeline (debug)
     RowMap map;                                                   // validity of q
     int act; float scale;
     const float* res; int ldres;
