@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsonata_b200.so")
+LIB_PATH = os.environ.get("SB200_LIB") or os.path.join(_HERE, "lib", "libsonata_b200.so")   # SB200_LIB: A/B builds
 
 
 class sb200_error(C.Structure):

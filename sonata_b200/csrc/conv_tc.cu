@@ -48,9 +48,6 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
 __device__ __forceinline__ void sts128u(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -137,10 +134,14 @@ __device__ __forceinline__ uint32_t split2(float a, float b, uint32_t& lo) {
     return hb;
 }
 
-// debug timeline: trace[(local tile) * 8 + slot] = clock64() for CTA 0, pipeline 0, first 48 tiles
-// slots: 0 producer issue, 1 producer landed, 2 producer converted, 3 mma a_full, 4 mma issued, 5 epi acc_full,
-//        6 epi tmem read, 7 epi stores issued
+// Optional per-role clock64() timeline (build with -DSB200_TC_TRACE_BUILD; see tools/trace_tc.py):
+// trace[(local tile) * 8 + slot] for CTA 0, pipeline 0, first 48 tiles.  slots: 0 producer issue, 1 landed,
+// 2 converted, 3 mma a_full, 4 mma issued, 5 epilogue acc_full, 6 TMEM read, 7 stores issued.
+#ifdef SB200_TC_TRACE_BUILD
 #define TC_TRACE(a, lt, slot) do { if ((a).trace && blockIdx.x == 0 && (lt) < 48) (a).trace[(lt) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define TC_TRACE(a, lt, slot) do { } while (0)
+#endif
 
 struct TcLaunch {
     int nt;          // columns per CTA tile (multiple of 32, <= 128)
@@ -151,8 +152,7 @@ struct TcLaunch {
     int tmem_cols;   // power of two >= 4*nt (two accumulator stages per pipeline)
     int ntiles_m, ntiles_n;
     uint32_t idesc;
-    int bulk_out;    // output tile rows are contiguous 128-B rows (C_out == ld == nt == 32): TMA bulk stores
-    int bulk_in;     // input rows are contiguous 128-B rows (ldx == 32): windows come in by one TMA bulk copy
+    int bulk_in;     // input rows are contiguous 128-B rows (ldx == 32): a window is ONE block -> one TMA bulk copy
 };
 
 constexpr int TC_MAXCH = 7;             // 32-B input pieces per producer thread per stage (win <= 224 rows)
@@ -163,8 +163,6 @@ constexpr int TC2_THREADS = 640;        // w0/w1 MMA issuers, w2/w3 weight produ
                                         // w12-15 / w16-19 epilogue groups (pipeline 0 / 1)
 constexpr int TC_MAX_ASTAGES = 4;       // per pipeline
 constexpr int TC_MAX_WRING = 44;        // barrier slots for the resident weight set (or 2 x ring)
-constexpr int TC_BAR_BYTES = 1024;      // mbarriers + TMEM slot
-constexpr int TC_STG_BYTES = 8 * 4096;  // per-epilogue-warp staging tiles for bulk stores
 
 // The CTA runs TWO independent half-pipelines (p = 0 / 1 own tiles tl = p, p+2, ...): one thread can issue an
 // M=128 MMA only every ~83 cycles whatever N is, while two issuing warps double the aggregate rate
@@ -187,7 +185,6 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
     uint64_t* acc_empty = acc_full + 4;                    // [4]
     uint64_t* raw_full = acc_empty + 4;                    // [2][TC_MAX_ASTAGES] bulk-loaded raw windows
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_full + 2 * TC_MAX_ASTAGES);
-    uint8_t* STG0 = reinterpret_cast<uint8_t*>(bars) + TC_BAR_BYTES;   // [8 epilogue warps][4 KB] (bulk_out only)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nkb = a.cin / 32;
@@ -325,8 +322,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
             const uint32_t img = smem_u32(Ap + (size_t)as * a_buf);
             const float* xk = a.x + kb * 32;
             if (L.bulk_in && rbase >= 0 && rbase + L.win <= a.rows_in) {
-                // 32-channel rows are contiguous: the whole window is ONE block -> TMA bulk copy.  This keeps the
-                // window traffic out of the LSU / L1 miss queue, where the epilogue's loads would wait behind it.
+                // contiguous 32-channel rows: the whole window is one block -> one TMA bulk copy (keeps the window
+                // traffic out of the LSU / L1 miss queue; measured +1.4 %)
                 if (gt == 0) {
                     mbar_expect_tx(smem_u32(&raw_full[p * TC_MAX_ASTAGES + as]), a_buf);
                     bulk_g2s(img, xk + (size_t)rbase * 32, a_buf, smem_u32(&raw_full[p * TC_MAX_ASTAGES + as]));
@@ -431,15 +428,13 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                 if (a.phase_cols) { orow += (size_t)(n / a.phase_cols); n %= a.phase_cols; }
                 const bool lo_side = n < a.split;
                 const bool accum = lo_side ? a.acc0 : a.acc1;
-                // Without read-modify-write the residual stays RAW in registers (no arithmetic before the accumulator
-                // is awaited, so the loads overlap the wait); with RMW both operands are folded into m = res*scale + prev.
 #pragma unroll
                 for (int j = 0; j < 32; j++) m[j] = 0.f;
                 if (a.res && live) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 r = *reinterpret_cast<const float4*>(a.res + orow * a.ldres + n + j);
-                        m[j] = r.x; m[j + 1] = r.y; m[j + 2] = r.z; m[j + 3] = r.w;
+                        m[j] = r.x * a.scale; m[j + 1] = r.y * a.scale; m[j + 2] = r.z * a.scale; m[j + 3] = r.w * a.scale;
                     }
                 }
                 if (accum && live) {
@@ -447,8 +442,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 r = *reinterpret_cast<const float4*>(src + j);
-                        m[j] = fmaf(m[j], a.scale, r.x); m[j + 1] = fmaf(m[j + 1], a.scale, r.y);
-                        m[j + 2] = fmaf(m[j + 2], a.scale, r.z); m[j + 3] = fmaf(m[j + 3], a.scale, r.w);
+                        m[j] += r.x; m[j + 1] += r.y; m[j + 2] += r.z; m[j + 3] += r.w;
                     }
                 }
             };
@@ -495,34 +489,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
 #pragma unroll
                     for (int j = 0; j < 32; j++) o[j] = fmaxf(o[j], 0.f);
                 }
-                if (L.bulk_out) {
-                    // Contiguous 32-column rows: this warp's 32 rows are one 4 KB block in HBM.  Stage them linearly
-                    // in smem and let the TMA write them (one cp.async.bulk instead of 8 row-per-thread STG.128,
-                    // each of which touches 32 different cache lines).  Gap rows get zeros (their invariant value).
-                    const uint32_t sbase = smem_u32(STG0 + (size_t)(warp - TC_EPI0) * 4096);
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous store done reading
-                    __syncwarp();
-#pragma unroll
-                    for (int c = 0; c < 8; c++) {
-                        float4 v;
-                        v.x = !valid ? 0.f : accum ? fmaf(o[4 * c], a.scale, m[4 * c]) : (o[4 * c] + m[4 * c]) * a.scale;
-                        v.y = !valid ? 0.f : accum ? fmaf(o[4 * c + 1], a.scale, m[4 * c + 1]) : (o[4 * c + 1] + m[4 * c + 1]) * a.scale;
-                        v.z = !valid ? 0.f : accum ? fmaf(o[4 * c + 2], a.scale, m[4 * c + 2]) : (o[4 * c + 2] + m[4 * c + 2]) * a.scale;
-                        v.w = !valid ? 0.f : accum ? fmaf(o[4 * c + 3], a.scale, m[4 * c + 3]) : (o[4 * c + 3] + m[4 * c + 3]) * a.scale;
-                        sts128(sbase + (uint32_t)lane * 128u + (uint32_t)c * 16u, v);
-                    }
-                    fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        float* gdst = a.y0 + (size_t)(q - lane) * 32;
-                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sbase), "r"(4096u) : "memory");
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
-                    continue;
-                }
                 if (accum && !valid) continue;     // accumulated buffers keep their zeros in gap rows
 #pragma unroll
-                for (int j = 0; j < 32; j++) o[j] = !valid ? 0.f : accum ? fmaf(o[j], a.scale, m[j]) : (o[j] + m[j]) * a.scale;
+                for (int j = 0; j < 32; j++) o[j] = valid ? fmaf(o[j], a.scale, m[j]) : 0.f;
                 float* dst = lo_side ? a.y0 + orow * a.ldy0 + n : a.y1 + orow * a.ldy1 + (n - a.split);
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
@@ -531,7 +500,6 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
             if (p == 0 && warp == TC_EPI0 && lane == 0) TC_TRACE(a, lt, 7);
         }
     }
-    if (L.bulk_out && warp >= TC_EPI0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -555,11 +523,8 @@ bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem) {
     const size_t w_stage = (size_t)L.nt * 128;
     const int per_tile = (a.cin / 32) * a.ntaps;
     const size_t budget = 225 * 1024 - 2048;
-    static_assert((2 * TC_MAX_WRING + 6 * TC_MAX_ASTAGES + 8) * 8 + 16 <= TC_BAR_BYTES, "barrier block");
-    L.bulk_out = (getenv("SB200_TC_BULKOUT") != nullptr && L.nt == 32 && a.cout == 32 && a.ldy0 == 32 && a.split >= a.cout && a.orow_mul == 1 &&
-                  a.orow_add == 0 && a.phase_cols == 0 && a.act != ACT_GATE) ? 1 : 0;
+    const size_t bar_bytes = (2 * TC_MAX_WRING + 6 * TC_MAX_ASTAGES + 8) * 8 + 16;
     L.bulk_in = (getenv("SB200_TC_NOBULKIN") == nullptr && a.ldx == 32 && a.cin == 32) ? 1 : 0;
-    const size_t bar_bytes = TC_BAR_BYTES + (L.bulk_out ? TC_STG_BYTES : 0);
     L.resident = (L.ntiles_n == 1 && per_tile <= TC_MAX_WRING && per_tile * w_stage + 4 * a_buf + bar_bytes <= budget) ? 1 : 0;
     L.ws = L.resident ? per_tile : (per_tile < 4 ? per_tile : 4);
     if (!L.resident && L.ws < 2) L.ws = 2;

@@ -202,6 +202,31 @@ def test_streaming_chunks_match_oracle(voice_paths, oracle_weights, tmp_path):
     m.close()
 
 
+def test_concurrent_calls_are_reentrant(models):
+    """The reference calls `speak_one_sentence` concurrently from rayon workers on ONE model
+    (synth/src/lib.rs:316-320): every call must own its stream / workspace."""
+    import threading
+    m = models("medium"); _det(m)
+    sents = [workload.synthetic_ids(n, utt=200 + i) for i, n in enumerate((20, 33, 9, 41, 15, 28, 37, 12))]
+    expect = [m.infer_with_values(s).samples.as_slice().copy() for s in sents]
+    got = [None] * len(sents)
+    errs = []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                got[i] = m.infer_with_values(sents[i]).samples.as_slice().copy()
+        except Exception as e:      # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(len(sents))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    for e, g in zip(expect, got):
+        assert g is not None and np.array_equal(e, g)
+
+
 def test_smoke_entry():
     import __graft_entry__ as ge
     ge.smoke()

@@ -99,7 +99,7 @@ def test_facade_speak_modes(lib_built, voice_paths, tmp_path):
         assert err.code == 0
         assert events[-1][0] == 1 and all(e[0] == 0 for e in events[:-1])          # SPEECH..., FINISHED
         speech = [e[1] for e in events[:-1]]
-        assert all(np.abs(s).max() == 32767 for s in speech if len(s))             # per-chunk peak normalisation
+        assert all(np.abs(s).max() >= 32766 for s in speech if len(s))             # per-chunk peak normalisation (truncating cast)
         totals[mode] = sum(len(s) for s in speech)
         assert totals[mode] % 256 == 0
     assert totals[0] == totals[1] == totals[2]                                     # same frames in every mode
