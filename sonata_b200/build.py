@@ -8,11 +8,12 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(os.path.dirname(HERE), "build", "obj")
-LIB = os.path.join(HERE, "lib", "libsonata_b200.so")
+OBJ = os.path.join(os.path.dirname(HERE), "build", os.environ.get("SB200_OBJ_DIR", "obj"))
+LIB = os.environ.get("SB200_LIB_OUT") or os.path.join(HERE, "lib", "libsonata_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unused-function"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unused-function"] + \
+        os.environ.get("SB200_NVCC_EXTRA", "").split()     # e.g. -DSB200_TC_TRACE_BUILD (tools/trace_tc.py)
 
 
 def _newer(src: str, dst: str, deps) -> bool:

@@ -41,6 +41,7 @@ struct ConvArgs {
     const float* x; int ldx; int rows_in; int cin; float in_slope;
     const float* w; const float* bias; int ldw; int cout;
     const float* wtc; int tc_nt;                                  // tcgen05 weight images (conv_tc.cu) or null
+    const float* wts;                                             // tap-stacked weight images (conv_ts.cu) or null
     int ntaps; int tap_off[SB_MAX_TAPS]; int min_off; int span;   // span = max_off - min_off
     int rows_q; int orow_mul; int orow_add;
     int phase_cols;                                               // >0: fused polyphase ConvTranspose (tcgen05 path only)
@@ -57,7 +58,12 @@ int conv_simt_bn_for(int cout);
 bool conv_tc_supported(const ConvArgs& a);
 void launch_conv_tc(const ConvArgs& a, cudaStream_t st);
 size_t conv_tc_weight_floats(int cin, int cout, int ntaps, int nt);
-void conv_tc_build_weights(const float* wt, int ldw, int cin, int cout, int ntaps, int nt, float* out);      // column tile the SIMT kernel will use for this cout (for weight padding)
+void conv_tc_build_weights(const float* wt, int ldw, int cin, int cout, int ntaps, int nt, float* out);
+bool conv_ts_supported(const ConvArgs& a);
+void launch_conv_ts(const ConvArgs& a, cudaStream_t st);
+size_t conv_ts_weight_floats(int ntaps);
+void conv_ts_build_weights(const float* wt, int ldw, int ntaps, float* out);
+      // column tile the SIMT kernel will use for this cout (for weight padding)
 
 // ---- misc kernels (kernels_misc.cu) ----
 void launch_embed(const int* ids_rows, const float* emb, float scale, float* x, int rows, int H, cudaStream_t st);

@@ -31,9 +31,7 @@
 // Warps: w0/w1 MMA issuers on alternating tiles (w0 also allocates TMEM), w2 weight producer, w4-7 / w8-11
 // two activation-producer groups, w12-15 / w16-19 two epilogue groups (one per half-pipeline).  Every mbarrier wait carries a watchdog that traps instead of
 // hanging the GPU.
-#include "common.cuh"
-#include <cuda_bf16.h>
-#include <stdio.h>
+#include "tc_common.cuh"
 #include <stdlib.h>
 #include <string.h>
 
@@ -41,107 +39,7 @@ namespace sb200 {
 
 namespace {
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts128u(uint32_t addr, uint4 v) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    unsigned spins = 0;
-    unsigned long long t0 = 0;
-    while (!mbar_try(bar, parity)) {
-        if ((++spins & 1023u) != 0) continue;
-        unsigned long long now;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
-        if (t0 == 0) t0 = now;
-        if (now - t0 > 2000000000ull) {   // 2 s: a pipeline bug must fail loudly, never hang the GPU
-            printf("conv_tc: mbarrier watchdog (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar,
-                   parity);
-            asm volatile("trap;");
-        }
-    }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
-        "elect.sync rx|px, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, px;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-// pack (hi, lo) halves of two consecutive channels with the packed converter (one cvt.rn.bf16x2.f32 per
-// pair instead of two scalar converts): returns the hi pair, writes the lo pair
-__device__ __forceinline__ uint32_t split2(float a, float b, uint32_t& lo) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
-    const float ha = __uint_as_float(hb << 16), hbf = __uint_as_float(hb & 0xffff0000u);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hbf);
-    lo = *reinterpret_cast<const uint32_t*>(&l);
-    return hb;
-}
-
-// Optional per-role clock64() timeline (build with -DSB200_TC_TRACE_BUILD; see tools/trace_tc.py):
-// trace[(local tile) * 8 + slot] for CTA 0, pipeline 0, first 48 tiles.  slots: 0 producer issue, 1 landed,
-// 2 converted, 3 mma a_full, 4 mma issued, 5 epilogue acc_full, 6 TMEM read, 7 stores issued.
-#ifdef SB200_TC_TRACE_BUILD
-#define TC_TRACE(a, lt, slot) do { if ((a).trace && blockIdx.x == 0 && (lt) < 48) (a).trace[(lt) * 8 + (slot)] = clock64(); } while (0)
-#else
-#define TC_TRACE(a, lt, slot) do { } while (0)
-#endif
+using namespace tcx;
 
 struct TcLaunch {
     int nt;          // columns per CTA tile (multiple of 32, <= 128)
@@ -562,6 +460,7 @@ static int tc_num_sms() {
 }
 
 void launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
+    if (conv_ts_supported(a)) { launch_conv_ts(a, st); return; }      // 32-channel layers: tap-stacked kernel
     TcLaunch L; size_t smem;
     if (!plan(a, L, smem)) { launch_conv_simt(a, st); return; }
     static bool attr_done = false;

@@ -71,11 +71,23 @@ CASES = [
     (20480, 192, 384, 5, 1, 1.0, 2, False, 1.0, False, 20000),
     (20480 + 128, 192, 384, 1, 1, 1.0, 0, False, 1.0, True, None),
     (9 * 148 * 128 // 4, 128, 128, 3, 2, 0.1, 0, True, 1.0, False, None),
+    # tap-stacked 32-channel kernel (conv_ts.cu): every (k, dilation) of ResBlock2 / ResBlock1, ragged tails,
+    # accumulate / residual / scale, many tiles per CTA on both accumulator stages
+    (300, 32, 32, 3, 2, 0.1, 0, True, 1.0, False, 290),
+    (1000, 32, 32, 5, 2, 0.1, 0, True, 1.0, False, 777),
+    (1000, 32, 32, 5, 6, 0.1, 0, True, 1 / 3, True, 999),
+    (1000, 32, 32, 7, 3, 0.1, 0, True, 1.0, False, None),
+    (148 * 56 * 5 + 17, 32, 32, 7, 12, 0.1, 0, True, 1 / 3, True, 148 * 56 * 5),
+    (148 * 126 * 4 + 100, 32, 32, 3, 1, 0.1, 0, True, 1.0, False, None),
+    (148 * 110 * 3 + 5, 32, 32, 7, 5, 0.1, 1, False, 1.0, False, None),
+    (40000, 32, 32, 11, 1, 0.1, 0, True, 1.0, False, None),      # k > 8: falls back to conv_tc
 ]
 
 if __name__ == "__main__":
     backend = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-    cases = CASES[:3] if len(sys.argv) > 2 else CASES
+    cases = CASES
+    if len(sys.argv) > 2:      # "quick" = first three cases, or a comma-separated list of case indices
+        cases = CASES[:3] if sys.argv[2] == "quick" else [CASES[int(i)] for i in sys.argv[2].split(",")]
     worst = 0.0
     for c in cases:
         e, msg = run_case(backend, *c)
