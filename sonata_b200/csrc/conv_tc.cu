@@ -55,6 +55,8 @@ struct TcLaunch {
     int tq;          // output rows per tile (128 normally; 128 - (slots-1)*dil when stacked)
     int slots;       // taps stacked along N
     int dil;         // tap spacing in rows
+    int depth;       // window loads in flight per pipeline (< na: see plan())
+    int v8;          // every epilogue operand is 32-byte aligned: 256-bit global accesses
 };
 
 constexpr int TC_MAXCH = 7;             // 32-B input pieces per producer thread per stage (win <= 224 rows)
@@ -218,7 +220,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
         uint8_t* Ap = A0 + (size_t)p * L.na * a_buf;
         const int nloc = (my_tiles - p + 1) / 2;       // tiles owned by this pipeline
         const int nst = nloc * nkb;                    // stages to produce
-        const int depth = L.na - 1;                    // stages in flight
+        const int depth = L.depth;                     // stages in flight
         auto issue_stage = [&](int j) {
             const int lt = j / nkb, kb = j - lt * nkb;
             const int tg = (int)blockIdx.x + (p + 2 * lt) * (int)gridDim.x;
@@ -337,16 +339,20 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                     for (int j = 0; j < 16; j++) m[j] = 0.f;
                     if (a.res && valid) {
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            const float4 r = *reinterpret_cast<const float4*>(a.res + orow * a.ldres + h * 16 + j);
-                            m[j] = r.x * a.scale; m[j + 1] = r.y * a.scale; m[j + 2] = r.z * a.scale; m[j + 3] = r.w * a.scale;
+                        for (int j = 0; j < 16; j += 8) {
+                            float r[8];
+                            ldg256(a.res + orow * a.ldres + h * 16 + j, r);
+#pragma unroll
+                            for (int e = 0; e < 8; e++) m[j + e] = r[e] * a.scale;
                         }
                     }
                     if (a.acc0 && valid) {
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            const float4 r = *reinterpret_cast<const float4*>(a.y0 + orow * a.ldy0 + h * 16 + j);
-                            m[j] += r.x; m[j + 1] += r.y; m[j + 2] += r.z; m[j + 3] += r.w;
+                        for (int j = 0; j < 16; j += 8) {
+                            float r[8];
+                            ldg256(a.y0 + orow * a.ldy0 + h * 16 + j, r);
+#pragma unroll
+                            for (int e = 0; e < 8; e++) m[j + e] += r[e];
                         }
                     }
                 };
@@ -402,9 +408,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
 #pragma unroll
                         for (int j = 0; j < 16; j++) o[j] = valid ? fmaf(o[j], a.scale, mc[j]) : 0.f;
                         float* dst = a.y0 + orow * a.ldy0 + h * 16;
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4)
-                            *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                        stg256(dst, o);
+                        stg256(dst + 8, o + 8);
                     }
 #pragma unroll
                     for (int j = 0; j < 16; j++) mc[j] = mn[j];
@@ -435,18 +440,31 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
 #pragma unroll
                 for (int j = 0; j < 32; j++) m[j] = 0.f;
                 if (a.res && live) {
+                    const float* src = a.res + orow * a.ldres + n;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 r = *reinterpret_cast<const float4*>(a.res + orow * a.ldres + n + j);
-                        m[j] = r.x * a.scale; m[j + 1] = r.y * a.scale; m[j + 2] = r.z * a.scale; m[j + 3] = r.w * a.scale;
+                    for (int j = 0; j < 32; j += 8) {
+                        float r[8];
+                        if (L.v8) ldg256(src + j, r);
+                        else {
+                            const float4 r0 = *reinterpret_cast<const float4*>(src + j), r1 = *reinterpret_cast<const float4*>(src + j + 4);
+                            r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w; r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; e++) m[j + e] = r[e] * a.scale;
                     }
                 }
                 if (accum && live) {
                     const float* src = lo_side ? a.y0 + orow * a.ldy0 + n : a.y1 + orow * a.ldy1 + (n - a.split);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 r = *reinterpret_cast<const float4*>(src + j);
-                        m[j] += r.x; m[j + 1] += r.y; m[j + 2] += r.z; m[j + 3] += r.w;
+                    for (int j = 0; j < 32; j += 8) {
+                        float r[8];
+                        if (L.v8) ldg256(src + j, r);
+                        else {
+                            const float4 r0 = *reinterpret_cast<const float4*>(src + j), r1 = *reinterpret_cast<const float4*>(src + j + 4);
+                            r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w; r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; e++) m[j + e] += r[e];
                     }
                 }
             };
@@ -480,12 +498,16 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                 if (gate) {
                     float* dst = a.y0 + orow * a.ldy0 + (n >> 1);
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        float g[4];
+                    for (int j = 0; j < 16; j += 8) {
+                        float g[8];
 #pragma unroll
-                        for (int e = 0; e < 4; e++)
+                        for (int e = 0; e < 8; e++)
                             g[e] = valid ? tanhf(o[2 * (j + e)]) * (1.f / (1.f + expf(-o[2 * (j + e) + 1]))) * a.scale : 0.f;
-                        *reinterpret_cast<float4*>(dst + j) = make_float4(g[0], g[1], g[2], g[3]);
+                        if (L.v8) stg256(dst + j, g);
+                        else {
+                            *reinterpret_cast<float4*>(dst + j) = make_float4(g[0], g[1], g[2], g[3]);
+                            *reinterpret_cast<float4*>(dst + j + 4) = make_float4(g[4], g[5], g[6], g[7]);
+                        }
                     }
                     continue;
                 }
@@ -498,8 +520,13 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                 for (int j = 0; j < 32; j++) o[j] = valid ? fmaf(o[j], a.scale, m[j]) : 0.f;
                 float* dst = lo_side ? a.y0 + orow * a.ldy0 + n : a.y1 + orow * a.ldy1 + (n - a.split);
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                for (int j = 0; j < 32; j += 8) {
+                    if (L.v8) stg256(dst + j, o + j);
+                    else {
+                        *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                        *reinterpret_cast<float4*>(dst + j + 4) = make_float4(o[j + 4], o[j + 5], o[j + 6], o[j + 7]);
+                    }
+                }
             }
             if (p == 0 && warp == TC_EPI0 && lane == 0) TC_TRACE(a, lt, 7);
         }
@@ -513,10 +540,21 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
     }
 }
 
+// 256-bit epilogue accesses need 32-byte aligned rows and column blocks for every operand that is used
+bool epi_v8_ok(const ConvArgs& a) {
+    if (getenv("SB200_TC_NOV8")) return false;
+    auto al = [](const void* p, int ld) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 31) == 0 && (ld & 7) == 0); };
+    const int half = a.act == ACT_GATE ? 2 : 1;       // the gate halves the column index
+    if (a.split % (8 * half) != 0 && a.split < a.cout) return false;
+    if (a.phase_cols && (a.phase_cols & 7)) return false;
+    return al(a.res, a.ldres) && al(a.y0, a.ldy0) && al(a.y1, a.ldy1);
+}
+
 bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem) {
     if (!a.wtc || a.tc_nt <= 0 || a.tc_nt > 128) return false;
     L.nt = a.tc_nt;
     L.tq = 128; L.slots = 1; L.dil = 1;
+    L.v8 = epi_v8_ok(a) ? 1 : 0;
     L.win = (128 + a.span + 7) & ~7;
     if (L.win * 4 > TC_MAXCH * TC_GROUP) return false;
     L.tmem_cols = 32;
@@ -540,6 +578,8 @@ bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem) {
     while (L.na > 2 && total() > budget) L.na--;
     while (!L.resident && L.ws > 2 && total() > budget) L.ws--;
     if (total() > budget) return false;
+    L.depth = L.na - 1;
+    { const char* e = getenv("SB200_TC_DEPTH"); if (e && atoi(e) >= 1 && atoi(e) < L.na) L.depth = atoi(e); }
     smem = total() + 2048;
     return true;
 }
@@ -553,7 +593,7 @@ bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem) {
 bool plan_stk(const ConvArgs& a, ConvArgs& v, TcLaunch& L, size_t& smem) {
     if (!a.wts || a.cin != 32 || a.cout != 32 || a.ntaps < 3 || a.ntaps > 16) return false;
     if (a.orow_mul != 1 || a.phase_cols || a.act == ACT_GATE || a.split < a.cout) return false;
-    if (!getenv("SB200_STK")) return false;
+    if (!getenv("SB200_STK") || !epi_v8_ok(a)) return false;
     const int dil = a.tap_off[1] - a.tap_off[0];
     if (dil < 1) return false;
     for (int t = 0; t < a.ntaps; t++) if (a.tap_off[t] != a.min_off + t * dil) return false;
@@ -582,6 +622,8 @@ bool plan_stk(const ConvArgs& a, ConvArgs& v, TcLaunch& L, size_t& smem) {
     auto total = [&]() { return (size_t)2 * L.na * a_buf + (size_t)ng * w_stage + 2 * TC_EX_BYTES + bar_bytes; };
     while (L.na > 2 && total() > budget) L.na--;
     if (total() > budget) return false;
+    L.depth = L.na - 1;
+    { const char* e = getenv("SB200_TC_DEPTH"); if (e && atoi(e) >= 1 && atoi(e) < L.na) L.depth = atoi(e); }
     smem = total() + 2048;
     return true;
 }

@@ -91,6 +91,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256).  In a row-per-thread epilogue the lanes of a warp touch
+// 32 different rows, so nothing coalesces ACROSS lanes: a 128-bit access moves half a 32-byte sector per request
+// and L2 sector throughput, not HBM, bounds the kernel.  One 256-bit access per thread is a whole sector.
+__device__ __forceinline__ void ldg256(const float* p, float* r) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]) : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, const float* r) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]),
+                 "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]) : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
     asm volatile(
