@@ -281,10 +281,16 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
             for (int u = 0; u < TC_MAXCH; u++) {
                 const int idx = gt + u * TC_GROUP;
                 const bool live = idx < npiece;        // warp-uniform per u except in the last partial warp
+                // Bank-conflict-free order: the 8 lanes of a quarter-warp cover two rows; odd rows take their two
+                // 16-byte chunks in the opposite order, so the 8 accesses of one instruction hit 8 different bank
+                // groups (shared-memory bandwidth, shared with the tensor core's operand fetch, bounds these layers).
+                const uint32_t odd = (uint32_t)(idx >> 2) & 1u;
                 float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
                 if (live) {
-                    v0 = lds128(img + (uint32_t)idx * 32u);
-                    v1 = lds128(img + (uint32_t)idx * 32u + 16u);
+                    const float4 t0 = lds128(img + (uint32_t)idx * 32u + odd * 16u);
+                    const float4 t1 = lds128(img + (uint32_t)idx * 32u + 16u - odd * 16u);
+                    v0 = odd ? t1 : t0;
+                    v1 = odd ? t0 : t1;
                 }
                 __syncwarp();                          // every lane of the row has read before anyone overwrites
                 if (live) {
@@ -301,8 +307,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                     hi.w = split2(e[6], e[7], lo.w);
                     const uint32_t rowb = (uint32_t)r * 128u;
                     const uint32_t sw = (uint32_t)(r & 7);
-                    sts128u(img + rowb + (((uint32_t)c ^ sw) << 4), hi);
-                    sts128u(img + rowb + (((uint32_t)(c + 4) ^ sw) << 4), lo);
+                    const uint4 first = odd ? lo : hi, second = odd ? hi : lo;      // same trick for the two stores
+                    sts128u(img + rowb + (((uint32_t)(c + 4 * odd) ^ sw) << 4), first);
+                    sts128u(img + rowb + (((uint32_t)(c + 4 - 4 * odd) ^ sw) << 4), second);
                 }
             }
             fence_async_smem();                       // generic-proxy stores -> visible to the tensor core
