@@ -32,6 +32,7 @@
 // two activation-producer groups, w12-15 / w16-19 two epilogue groups (one per half-pipeline).  Every mbarrier wait carries a watchdog that traps instead of
 // hanging the GPU.
 #include "tc_common.cuh"
+#include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -57,6 +58,7 @@ struct TcLaunch {
     int dil;         // tap spacing in rows
     int depth;       // window loads in flight per pipeline (< na: see plan())
     int v8;          // every epilogue operand is 32-byte aligned: 256-bit global accesses
+    int tma_st;      // MODE 2: output tile leaves through a TMA tensor store
 };
 
 constexpr int TC_MAXCH = 7;             // 32-B input pieces per producer thread per stage (win <= 224 rows)
@@ -70,13 +72,19 @@ constexpr int TC_MAX_WRING = 44;        // barrier slots for the resident weight
 constexpr int TC_EX_STRIDE = 80;        // stacked mode: bytes per row of the slot-exchange buffer (16 floats + 16 B pad:
                                         // 128-bit accesses of 8 consecutive rows hit 8 different bank groups)
 constexpr int TC_EX_BYTES = 128 * TC_EX_STRIDE;
+constexpr int TC_OUT_BYTES = 128 * 128;  // MODE 2: one staged output tile (128 rows x 32 fp32), two per pipeline
 
 // The CTA runs TWO independent half-pipelines (p = 0 / 1 own tiles tl = p, p+2, ...): one thread can issue an
 // M=128 MMA only every ~83 cycles whatever N is, while two issuing warps double the aggregate rate
 // (tools/micro/mma_bench.cu: N=32 385 -> 774 MAC/clk/SM, N=128 1572 -> 2046 = peak).  Each pipeline has its
 // own activation ring, weight ring and accumulator pair, so no mbarrier can be lapped by the other pipeline.
-template <bool STK>
-__global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs a, const TcLaunch L) {
+// MODE 0: plain mapping (one tap per MMA, N = nt).  MODE 1: stacked taps (experimental, see plan_stk()).
+// MODE 2: plain mapping for 32-channel outputs with the tile written by ONE TMA tensor store from a swizzled
+// shared-memory staging tile (see the epilogue).
+template <int MODE>
+__global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs a, const TcLaunch L,
+                                                                  const __grid_constant__ CUtensorMap tm_out) {
+    constexpr bool STK = MODE == 1;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t a_buf = (uint32_t)L.win * 128u;              // one [hi|lo] window image
@@ -85,7 +93,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
     uint8_t* A0 = smem;                                         // [2][na] stages
     uint8_t* W0 = A0 + (size_t)2 * L.na * a_buf;                // resident: [ws]; ring: [2][ws]
     uint8_t* EX = W0 + (size_t)wslots * w_stage;                // stacked mode: [2 pipelines] slot-exchange buffers
-    uint64_t* bars = reinterpret_cast<uint64_t*>(EX + (STK ? 2 * TC_EX_BYTES : 0));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(EX + (STK ? 2 * TC_EX_BYTES : MODE == 2 ? 4 * TC_OUT_BYTES : 0));
     uint64_t* w_full = bars;                               // [TC_MAX_WRING]
     uint64_t* w_empty = w_full + TC_MAX_WRING;             // [TC_MAX_WRING]
     uint64_t* a_full = w_empty + TC_MAX_WRING;             // [2][TC_MAX_ASTAGES]
@@ -423,6 +431,86 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                 }
                 if (p == 0 && warp == TC_EPI0 && lane == 0) TC_TRACE(a, lt, 7);
             }
+        } else if constexpr (MODE == 2) {
+            // ---- 32-channel output, row-per-thread math, but the tile leaves through the TMA engine: each thread
+            // writes its 128-byte row into a SWIZZLE_128B staging tile (16-byte chunk c of row r at c ^ (r & 7):
+            // conflict-free 128-bit stores) and one thread issues a tensor store for the whole tile.  A row-per-thread
+            // STG touches 32 different lines per instruction (one L1TEX data-pipe wavefront per thread); ncu showed
+            // that pipe 83 % busy, two thirds of it global wavefronts, while HBM and L2 sat at 40 %.
+            const uint32_t ob = smem_u32(EX + (size_t)p * 2 * TC_OUT_BYTES);
+            const bool leader = quad == 0 && lane == 0;
+            const uint32_t sw = (uint32_t)(row & 7);
+            for (int tl = p, lt = 0; tl < my_tiles; tl += 2, lt++) {
+                const int tg = (int)blockIdx.x + tl * (int)gridDim.x;
+                const int q = tg * 128 + row;
+                const int acc = p + 2 * (lt & 1);
+                const bool valid = q < a.rows_q && row_valid(a.map, q);
+                const size_t orow = (size_t)q + a.orow_add;
+                float m[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) m[j] = 0.f;
+                if (a.res && valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        float r[8];
+                        ldg256(a.res + orow * a.ldres + j, r);
+#pragma unroll
+                        for (int e = 0; e < 8; e++) m[j + e] = r[e] * a.scale;
+                    }
+                }
+                if (a.acc0 && valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        float r[8];
+                        ldg256(a.y0 + orow * a.ldy0 + j, r);
+#pragma unroll
+                        for (int e = 0; e < 8; e++) m[j + e] += r[e];
+                    }
+                }
+                mbar_wait(smem_u32(&acc_full[acc]), (uint32_t)((lt >> 1) & 1));
+                tc_fence_after();
+                if (p == 0 && warp == TC_EPI0 && lane == 0) TC_TRACE(a, lt, 5);
+                float o[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * L.nt), o);
+                tc_fence_before();
+                mbar_arrive(smem_u32(&acc_empty[acc]));
+                if (p == 0 && warp == TC_EPI0 && lane == 0) TC_TRACE(a, lt, 6);
+                if (a.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b = *reinterpret_cast<const float4*>(a.bias + j);
+                        o[j] += b.x; o[j + 1] += b.y; o[j + 2] += b.z; o[j + 3] += b.w;
+                    }
+                }
+                if (a.act == ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) o[j] = fmaxf(o[j], 0.f);
+                }
+                // gap rows are written as zeros (accumulated buffers hold zeros there already); rows past the end of
+                // the array are clipped by the tensor map
+                const uint32_t orow_s = ob + (uint32_t)(lt & 1) * TC_OUT_BYTES + (uint32_t)row * 128u;
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    uint4 u;
+                    u.x = __float_as_uint(valid ? fmaf(o[4 * c], a.scale, m[4 * c]) : 0.f);
+                    u.y = __float_as_uint(valid ? fmaf(o[4 * c + 1], a.scale, m[4 * c + 1]) : 0.f);
+                    u.z = __float_as_uint(valid ? fmaf(o[4 * c + 2], a.scale, m[4 * c + 2]) : 0.f);
+                    u.w = __float_as_uint(valid ? fmaf(o[4 * c + 3], a.scale, m[4 * c + 3]) : 0.f);
+                    sts128u(orow_s + (((uint32_t)c ^ sw) << 4), u);
+                }
+                fence_async_smem();                                  // generic-proxy stores -> visible to the TMA engine
+                // the staging tile written NOW is stored below; the other one (tile lt-1) must have been read out
+                // before anybody writes it again at tile lt+1: the leader checks that before the barrier
+                if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + p) : "memory");
+                if (leader) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                 ::"l"(&tm_out), "r"(ob + (uint32_t)(lt & 1) * TC_OUT_BYTES), "r"(0), "r"(tg * 128) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                if (p == 0 && warp == TC_EPI0 && lane == 0) TC_TRACE(a, lt, 7);
+            }
+            if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before the CTA retires
         } else {
         const int nch = L.nt / 32;
         const bool gate = a.act == ACT_GATE;
@@ -547,6 +635,36 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
     }
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TensorMapEncodeFn tensor_map_encoder() {
+    static TensorMapEncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<TensorMapEncodeFn>(p);
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+// [rows][32] fp32 view of an output buffer: 128 x 32 boxes, SWIZZLE_128B in shared memory
+bool make_out_map(CUtensorMap* tm, float* base, int rows, int ld) {
+    const cuuint64_t dims[2] = {32, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {32, 128};
+    const cuuint32_t estr[2] = {1, 1};
+    return tensor_map_encoder()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // 256-bit epilogue accesses need 32-byte aligned rows and column blocks for every operand that is used
 bool epi_v8_ok(const ConvArgs& a) {
     if (getenv("SB200_TC_NOV8")) return false;
@@ -562,6 +680,8 @@ bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem) {
     L.nt = a.tc_nt;
     L.tq = 128; L.slots = 1; L.dil = 1;
     L.v8 = epi_v8_ok(a) ? 1 : 0;
+    L.tma_st = (L.v8 && a.cout == 32 && L.nt == 32 && a.act != ACT_GATE && !a.phase_cols && a.split >= a.cout && a.orow_mul == 1 &&
+                tensor_map_encoder() != nullptr && !getenv("SB200_TC_NOTMAST")) ? 1 : 0;
     L.win = (128 + a.span + 7) & ~7;
     if (L.win * 4 > TC_MAXCH * TC_GROUP) return false;
     L.tmem_cols = 32;
@@ -574,7 +694,7 @@ bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem) {
     const size_t w_stage = (size_t)L.nt * 128;
     const int per_tile = (a.cin / 32) * a.ntaps;
     const size_t budget = 225 * 1024 - 2048;
-    const size_t bar_bytes = (2 * TC_MAX_WRING + 6 * TC_MAX_ASTAGES + 8) * 8 + 16;
+    const size_t bar_bytes = (2 * TC_MAX_WRING + 6 * TC_MAX_ASTAGES + 8) * 8 + 16 + (L.tma_st ? 4 * TC_OUT_BYTES : 0);
     L.bulk_in = (getenv("SB200_TC_NOBULKIN") == nullptr && a.ldx == 32 && a.cin == 32) ? 1 : 0;
     L.resident = (L.ntiles_n == 1 && per_tile <= TC_MAX_WRING && per_tile * w_stage + 4 * a_buf + bar_bytes <= budget) ? 1 : 0;
     L.ws = L.resident ? per_tile : (per_tile < 4 ? per_tile : 4);
@@ -662,15 +782,18 @@ void launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     if (conv_ts_supported(a)) { launch_conv_ts(a, st); return; }      // experimental transposed kernel (opt-in)
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_done = true;
     }
     TcLaunch L; size_t smem;
     ConvArgs v;
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));
     if (plan_stk(a, v, L, smem)) {                                    // experimental: four taps per MMA (opt-in)
         const int grid = L.ntiles_m < tc_num_sms() ? L.ntiles_m : tc_num_sms();
-        conv_tc_kernel<true><<<grid, TC2_THREADS, smem, st>>>(v, L);
+        conv_tc_kernel<1><<<grid, TC2_THREADS, smem, st>>>(v, L, tm);
         g_launch_count++;
         check_launch("conv_tc_stk");
         return;
@@ -678,7 +801,13 @@ void launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     if (!plan(a, L, smem)) { launch_conv_simt(a, st); return; }
     const int tiles = L.ntiles_m * L.ntiles_n;
     const int grid = tiles < tc_num_sms() ? tiles : tc_num_sms();
-    conv_tc_kernel<false><<<grid, TC2_THREADS, smem, st>>>(a, L);
+    if (L.tma_st && make_out_map(&tm, a.y0 + (size_t)a.orow_add * a.ldy0, a.rows_q, a.ldy0)) {
+        conv_tc_kernel<2><<<grid, TC2_THREADS, smem, st>>>(a, L, tm);
+        g_launch_count++;
+        check_launch("conv_tc_tma");
+        return;
+    }
+    conv_tc_kernel<0><<<grid, TC2_THREADS, smem, st>>>(a, L, tm);
     g_launch_count++;
     check_launch("conv_tc");
 }
