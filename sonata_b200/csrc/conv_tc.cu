@@ -42,6 +42,11 @@ namespace {
 
 using namespace tcx;
 
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+
 struct TcLaunch {
     int nt;          // columns per CTA tile (multiple of 32, <= 128)
     int win;         // window rows (multiple of 8)
@@ -83,7 +88,8 @@ constexpr int TC_OUT_BYTES = 128 * 128;  // MODE 2: one staged output tile (128 
 // shared-memory staging tile (see the epilogue).
 template <int MODE>
 __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs a, const TcLaunch L,
-                                                                  const __grid_constant__ CUtensorMap tm_out) {
+                                                                  const __grid_constant__ CUtensorMap tm_out,
+                                                                  const __grid_constant__ CUtensorMap tm_res) {
     constexpr bool STK = MODE == 1;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -101,7 +107,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
     uint64_t* acc_full = a_empty + 2 * TC_MAX_ASTAGES;     // [4]  (index = pipeline + 2 * stage)
     uint64_t* acc_empty = acc_full + 4;                    // [4]
     uint64_t* raw_full = acc_empty + 4;                    // [2][TC_MAX_ASTAGES] bulk-loaded raw windows
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_full + 2 * TC_MAX_ASTAGES);
+    uint64_t* staged = raw_full + 2 * TC_MAX_ASTAGES;      // [2] MODE 2: output tile staged by the 128 epilogue threads
+    uint64_t* epi_full = staged + 2;                       // [2] MODE 2: residual / previous-value tiles landed (TMA)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_full + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nkb = a.cin / 32;
@@ -113,6 +121,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
         for (int s = 0; s < wslots; s++) { mbar_init(smem_u32(&w_full[s]), 1); mbar_init(smem_u32(&w_empty[s]), 1); }
         for (int s = 0; s < 2 * TC_MAX_ASTAGES; s++) { mbar_init(smem_u32(&a_full[s]), TC_GROUP); mbar_init(smem_u32(&a_empty[s]), 1); mbar_init(smem_u32(&raw_full[s]), 1); }
         for (int s = 0; s < 4; s++) { mbar_init(smem_u32(&acc_full[s]), 1); mbar_init(smem_u32(&acc_empty[s]), 128); }
+        for (int s = 0; s < 2; s++) { mbar_init(smem_u32(&staged[s]), 128); mbar_init(smem_u32(&epi_full[s]), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -213,6 +222,33 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                         bulk_g2s(smem_u32(Wp + (size_t)ws * w_stage), wsrc + (size_t)i * w_stage, w_stage, smem_u32(&wf[ws]));
                     }
                 }
+            }
+        }
+        if constexpr (MODE == 2) {
+            // ---- TMA agent of pipeline p (the weight warps are idle once the resident weights are in): stores the
+            // staged output tile, waits until the engine has read it, then fetches the residual / previous-value
+            // tiles of the pipeline's next tile into the same staging buffers.  The epilogue threads never wait for
+            // a store and never touch global memory.
+            if (lane == 0) {
+                const uint32_t st = smem_u32(EX + (size_t)p * 2 * TC_OUT_BYTES);      // [0] residual-in / output, [1] previous
+                const uint32_t bytes = (a.res ? TC_OUT_BYTES : 0) + (a.acc0 ? TC_OUT_BYTES : 0);
+                auto fetch = [&](int tl) {
+                    if (!bytes) return;
+                    const int r0 = ((int)blockIdx.x + tl * (int)gridDim.x) * 128;
+                    mbar_expect_tx(smem_u32(&epi_full[p]), bytes);
+                    if (a.res) tma_load_2d(st, &tm_res, smem_u32(&epi_full[p]), 0, r0);
+                    if (a.acc0) tma_load_2d(st + TC_OUT_BYTES, &tm_out, smem_u32(&epi_full[p]), 0, r0);
+                };
+                if (p < my_tiles) fetch(p);
+                for (int tl = p, lt = 0; tl < my_tiles; tl += 2, lt++) {
+                    mbar_wait(smem_u32(&staged[p]), (uint32_t)(lt & 1));
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                 ::"l"(&tm_out), "r"(st), "r"(0), "r"(((int)blockIdx.x + tl * (int)gridDim.x) * 128) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    if (tl + 2 < my_tiles) fetch(tl + 2);
+                }
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before the CTA retires
             }
         }
         __syncwarp();
@@ -432,41 +468,21 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                 if (p == 0 && warp == TC_EPI0 && lane == 0) TC_TRACE(a, lt, 7);
             }
         } else if constexpr (MODE == 2) {
-            // ---- 32-channel output, row-per-thread math, but the tile leaves through the TMA engine: each thread
-            // writes its 128-byte row into a SWIZZLE_128B staging tile (16-byte chunk c of row r at c ^ (r & 7):
-            // conflict-free 128-bit stores) and one thread issues a tensor store for the whole tile.  A row-per-thread
-            // STG touches 32 different lines per instruction (one L1TEX data-pipe wavefront per thread); ncu showed
-            // that pipe 83 % busy, two thirds of it global wavefronts, while HBM and L2 sat at 40 %.
-            const uint32_t ob = smem_u32(EX + (size_t)p * 2 * TC_OUT_BYTES);
-            const bool leader = quad == 0 && lane == 0;
+            // ---- 32-channel output, row-per-thread math, but every global operand of the epilogue moves through the
+            // TMA engine: the residual and previous-value tiles arrive in SWIZZLE_128B staging tiles (16-byte chunk
+            // c of row r at c ^ (r & 7): conflict-free 128-bit accesses for a row-per-thread owner), the result is
+            // written over the residual tile in place and leaves with one tensor store issued by the agent warp.
+            // A row-per-thread LDG/STG touches 32 different lines per instruction (one L1TEX data-pipe wavefront
+            // per thread); ncu showed that pipe 83 % busy, two thirds of it global wavefronts, while HBM and L2
+            // sat at 40 %.
+            const uint32_t st = smem_u32(EX + (size_t)p * 2 * TC_OUT_BYTES) + (uint32_t)row * 128u;
             const uint32_t sw = (uint32_t)(row & 7);
+            const bool staged_in = a.res != nullptr || a.acc0;
             for (int tl = p, lt = 0; tl < my_tiles; tl += 2, lt++) {
                 const int tg = (int)blockIdx.x + tl * (int)gridDim.x;
                 const int q = tg * 128 + row;
                 const int acc = p + 2 * (lt & 1);
                 const bool valid = q < a.rows_q && row_valid(a.map, q);
-                const size_t orow = (size_t)q + a.orow_add;
-                float m[32];
-#pragma unroll
-                for (int j = 0; j < 32; j++) m[j] = 0.f;
-                if (a.res && valid) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        float r[8];
-                        ldg256(a.res + orow * a.ldres + j, r);
-#pragma unroll
-                        for (int e = 0; e < 8; e++) m[j + e] = r[e] * a.scale;
-                    }
-                }
-                if (a.acc0 && valid) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        float r[8];
-                        ldg256(a.y0 + orow * a.ldy0 + j, r);
-#pragma unroll
-                        for (int e = 0; e < 8; e++) m[j + e] += r[e];
-                    }
-                }
                 mbar_wait(smem_u32(&acc_full[acc]), (uint32_t)((lt >> 1) & 1));
                 tc_fence_after();
                 if (p == 0 && warp == TC_EPI0 && lane == 0) TC_TRACE(a, lt, 5);
@@ -486,31 +502,26 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
 #pragma unroll
                     for (int j = 0; j < 32; j++) o[j] = fmaxf(o[j], 0.f);
                 }
+                if (staged_in) mbar_wait(smem_u32(&epi_full[p]), (uint32_t)(lt & 1));
                 // gap rows are written as zeros (accumulated buffers hold zeros there already); rows past the end of
                 // the array are clipped by the tensor map
-                const uint32_t orow_s = ob + (uint32_t)(lt & 1) * TC_OUT_BYTES + (uint32_t)row * 128u;
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
+                    const uint32_t off = (((uint32_t)c ^ sw) << 4);
+                    float4 r = make_float4(0.f, 0.f, 0.f, 0.f), pv = r;
+                    if (a.res) r = lds128(st + off);
+                    if (a.acc0) pv = lds128(st + TC_OUT_BYTES + off);
                     uint4 u;
-                    u.x = __float_as_uint(valid ? fmaf(o[4 * c], a.scale, m[4 * c]) : 0.f);
-                    u.y = __float_as_uint(valid ? fmaf(o[4 * c + 1], a.scale, m[4 * c + 1]) : 0.f);
-                    u.z = __float_as_uint(valid ? fmaf(o[4 * c + 2], a.scale, m[4 * c + 2]) : 0.f);
-                    u.w = __float_as_uint(valid ? fmaf(o[4 * c + 3], a.scale, m[4 * c + 3]) : 0.f);
-                    sts128u(orow_s + (((uint32_t)c ^ sw) << 4), u);
+                    u.x = __float_as_uint(valid ? fmaf(o[4 * c] + r.x, a.scale, pv.x) : 0.f);
+                    u.y = __float_as_uint(valid ? fmaf(o[4 * c + 1] + r.y, a.scale, pv.y) : 0.f);
+                    u.z = __float_as_uint(valid ? fmaf(o[4 * c + 2] + r.z, a.scale, pv.z) : 0.f);
+                    u.w = __float_as_uint(valid ? fmaf(o[4 * c + 3] + r.w, a.scale, pv.w) : 0.f);
+                    sts128u(st + off, u);
                 }
                 fence_async_smem();                                  // generic-proxy stores -> visible to the TMA engine
-                // the staging tile written NOW is stored below; the other one (tile lt-1) must have been read out
-                // before anybody writes it again at tile lt+1: the leader checks that before the barrier
-                if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + p) : "memory");
-                if (leader) {
-                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                                 ::"l"(&tm_out), "r"(ob + (uint32_t)(lt & 1) * TC_OUT_BYTES), "r"(0), "r"(tg * 128) : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
+                mbar_arrive(smem_u32(&staged[p]));
                 if (p == 0 && warp == TC_EPI0 && lane == 0) TC_TRACE(a, lt, 7);
             }
-            if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before the CTA retires
         } else {
         const int nch = L.nt / 32;
         const bool gate = a.act == ACT_GATE;
@@ -682,6 +693,7 @@ bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem) {
     L.v8 = epi_v8_ok(a) ? 1 : 0;
     L.tma_st = (L.v8 && a.cout == 32 && L.nt == 32 && a.act != ACT_GATE && !a.phase_cols && a.split >= a.cout && a.orow_mul == 1 &&
                 tensor_map_encoder() != nullptr && !getenv("SB200_TC_NOTMAST")) ? 1 : 0;
+    if (a.res && (a.ldres & 3)) L.tma_st = 0;
     L.win = (128 + a.span + 7) & ~7;
     if (L.win * 4 > TC_MAXCH * TC_GROUP) return false;
     L.tmem_cols = 32;
@@ -694,7 +706,7 @@ bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem) {
     const size_t w_stage = (size_t)L.nt * 128;
     const int per_tile = (a.cin / 32) * a.ntaps;
     const size_t budget = 225 * 1024 - 2048;
-    const size_t bar_bytes = (2 * TC_MAX_WRING + 6 * TC_MAX_ASTAGES + 8) * 8 + 16 + (L.tma_st ? 4 * TC_OUT_BYTES : 0);
+    const size_t bar_bytes = (2 * TC_MAX_WRING + 6 * TC_MAX_ASTAGES + 12) * 8 + 16 + (L.tma_st ? 4 * TC_OUT_BYTES : 0);
     L.bulk_in = (getenv("SB200_TC_NOBULKIN") == nullptr && a.ldx == 32 && a.cin == 32) ? 1 : 0;
     L.resident = (L.ntiles_n == 1 && per_tile <= TC_MAX_WRING && per_tile * w_stage + 4 * a_buf + bar_bytes <= budget) ? 1 : 0;
     L.ws = L.resident ? per_tile : (per_tile < 4 ? per_tile : 4);
@@ -741,7 +753,7 @@ bool plan_stk(const ConvArgs& a, ConvArgs& v, TcLaunch& L, size_t& smem) {
     L.ntiles_n = 1;
     const size_t a_buf = (size_t)L.win * 128, w_stage = 128 * 128;
     const size_t budget = 225 * 1024 - 2048;
-    const size_t bar_bytes = (2 * TC_MAX_WRING + 6 * TC_MAX_ASTAGES + 8) * 8 + 16;
+    const size_t bar_bytes = (2 * TC_MAX_WRING + 6 * TC_MAX_ASTAGES + 12) * 8 + 16;
     L.bulk_in = (getenv("SB200_TC_NOBULKIN") == nullptr && a.ldx == 32) ? 1 : 0;
     L.resident = 1; L.ws = ng;
     L.na = TC_MAX_ASTAGES;
@@ -789,11 +801,12 @@ void launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     }
     TcLaunch L; size_t smem;
     ConvArgs v;
-    CUtensorMap tm;
+    CUtensorMap tm, tmr;
     memset(&tm, 0, sizeof(tm));
+    memset(&tmr, 0, sizeof(tmr));
     if (plan_stk(a, v, L, smem)) {                                    // experimental: four taps per MMA (opt-in)
         const int grid = L.ntiles_m < tc_num_sms() ? L.ntiles_m : tc_num_sms();
-        conv_tc_kernel<1><<<grid, TC2_THREADS, smem, st>>>(v, L, tm);
+        conv_tc_kernel<1><<<grid, TC2_THREADS, smem, st>>>(v, L, tm, tmr);
         g_launch_count++;
         check_launch("conv_tc_stk");
         return;
@@ -801,13 +814,14 @@ void launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     if (!plan(a, L, smem)) { launch_conv_simt(a, st); return; }
     const int tiles = L.ntiles_m * L.ntiles_n;
     const int grid = tiles < tc_num_sms() ? tiles : tc_num_sms();
-    if (L.tma_st && make_out_map(&tm, a.y0 + (size_t)a.orow_add * a.ldy0, a.rows_q, a.ldy0)) {
-        conv_tc_kernel<2><<<grid, TC2_THREADS, smem, st>>>(a, L, tm);
+    if (L.tma_st && L.resident && make_out_map(&tm, a.y0 + (size_t)a.orow_add * a.ldy0, a.rows_q, a.ldy0) &&
+        (!a.res || make_out_map(&tmr, const_cast<float*>(a.res) + (size_t)a.orow_add * a.ldres, a.rows_q, a.ldres))) {
+        conv_tc_kernel<2><<<grid, TC2_THREADS, smem, st>>>(a, L, tm, tmr);
         g_launch_count++;
         check_launch("conv_tc_tma");
         return;
     }
-    conv_tc_kernel<0><<<grid, TC2_THREADS, smem, st>>>(a, L, tm);
+    conv_tc_kernel<0><<<grid, TC2_THREADS, smem, st>>>(a, L, tm, tmr);
     g_launch_count++;
     check_launch("conv_tc");
 }
