@@ -233,7 +233,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                 const uint32_t st = smem_u32(EX + (size_t)p * 2 * TC_OUT_BYTES);      // [0] residual-in / output, [1] previous
                 const uint32_t bytes = (a.res ? TC_OUT_BYTES : 0) + (a.acc0 ? TC_OUT_BYTES : 0);
                 auto fetch = [&](int tl) {
-                    if (!bytes) return;
+                    // nothing to fetch: still publish "staging tile free" (the previous store has been read out)
+                    if (!bytes) { mbar_arrive(smem_u32(&epi_full[p])); return; }
                     const int r0 = ((int)blockIdx.x + tl * (int)gridDim.x) * 128;
                     mbar_expect_tx(smem_u32(&epi_full[p]), bytes);
                     if (a.res) tma_load_2d(st, &tm_res, smem_u32(&epi_full[p]), 0, r0);
@@ -477,7 +478,6 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
             // sat at 40 %.
             const uint32_t st = smem_u32(EX + (size_t)p * 2 * TC_OUT_BYTES) + (uint32_t)row * 128u;
             const uint32_t sw = (uint32_t)(row & 7);
-            const bool staged_in = a.res != nullptr || a.acc0;
             for (int tl = p, lt = 0; tl < my_tiles; tl += 2, lt++) {
                 const int tg = (int)blockIdx.x + tl * (int)gridDim.x;
                 const int q = tg * 128 + row;
@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
 #pragma unroll
                     for (int j = 0; j < 32; j++) o[j] = fmaxf(o[j], 0.f);
                 }
-                if (staged_in) mbar_wait(smem_u32(&epi_full[p]), (uint32_t)(lt & 1));
+                mbar_wait(smem_u32(&epi_full[p]), (uint32_t)(lt & 1));     // operands landed AND staging tile free
                 // gap rows are written as zeros (accumulated buffers hold zeros there already); rows past the end of
                 // the array are clipped by the tensor map
 #pragma unroll

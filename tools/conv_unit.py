@@ -81,6 +81,10 @@ CASES = [
     (148 * 126 * 4 + 100, 32, 32, 3, 1, 0.1, 0, True, 1.0, False, None),
     (148 * 110 * 3 + 5, 32, 32, 7, 5, 0.1, 1, False, 1.0, False, None),
     (40000, 32, 32, 11, 1, 0.1, 0, True, 1.0, False, None),      # k > 8: falls back to conv_tc
+    # TMA-staged epilogue (conv_tc MODE 2) with nothing to fetch: the staging tile is rewritten every tile, so the
+    # agent's "store has been read out" signal is the only thing that orders it (regression: WAR race)
+    (148 * 128 * 6 + 77, 32, 32, 3, 1, 0.1, 0, False, 1.0, False, None),
+    (148 * 128 * 4, 32, 32, 11, 5, 0.1, 0, False, 1.0, True, 148 * 128 * 4 - 1000),
 ]
 
 if __name__ == "__main__":
