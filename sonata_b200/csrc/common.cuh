@@ -42,6 +42,7 @@ struct ConvArgs {
     const float* w; const float* bias; int ldw; int cout;
     const float* wtc; int tc_nt;                                  // tcgen05 weight images (conv_tc.cu) or null
     const float* wts;                                             // tap-stacked weight images (conv_ts.cu) or null
+    const float* wcat;                                            // hi/lo-stacked tap-pair images (conv_tc.cu cat mode) or null
     int ntaps; int tap_off[SB_MAX_TAPS]; int min_off; int span;   // span = max_off - min_off
     int rows_q; int orow_mul; int orow_add;
     int phase_cols;                                               // >0: fused polyphase ConvTranspose (tcgen05 path only)
@@ -59,6 +60,8 @@ bool conv_tc_supported(const ConvArgs& a);
 void launch_conv_tc(const ConvArgs& a, cudaStream_t st);
 size_t conv_tc_weight_floats(int cin, int cout, int ntaps, int nt);
 void conv_tc_build_weights(const float* wt, int ldw, int cin, int cout, int ntaps, int nt, float* out);
+size_t conv_tc_cat_weight_floats(int cin, int cout, int ntaps, int nt);
+void conv_tc_build_weights_cat(const float* wt, int ldw, int cin, int cout, int ntaps, int nt, float* out);
 bool conv_ts_supported(const ConvArgs& a);
 void launch_conv_ts(const ConvArgs& a, cudaStream_t st);
 size_t conv_ts_weight_floats(int ntaps);

@@ -64,6 +64,14 @@ struct TcLaunch {
     int depth;       // window loads in flight per pipeline (< na: see plan())
     int v8;          // every epilogue operand is 32-byte aligned: 256-bit global accesses
     int tma_st;      // MODE 2: output tile leaves through a TMA tensor store
+    // "cat" mode (nt <= 64, resident weights): the weight image of a tap stacks the hi rows and the lo rows along N,
+    // so  A_hi x [W_hi ; W_lo]  is ONE MMA of N = 2*nt (columns [0,nt) = hi*hi, [nt,2nt) = hi*lo) and  A_lo x W_hi
+    // accumulates into the first nt columns: 2 MMAs instead of 3 per (tap, K-step).  One thread can issue an
+    // M=128 MMA only every ~85-100 cycles whatever N is, and once the epilogue traffic moved to the TMA engine
+    // the MMA issue loop was the longest stage of the 32-channel layers.  The epilogue adds the two column halves.
+    int cat;
+    int accw;        // TMEM columns per accumulator stage (nt, or 2*nt in cat mode)
+    uint32_t idesc2; // instruction descriptor with N = 2*nt
 };
 
 constexpr int TC_MAXCH = 7;             // 32-B input pieces per producer thread per stage (win <= 224 rows)
@@ -94,7 +102,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t a_buf = (uint32_t)L.win * 128u;              // one [hi|lo] window image
-    const uint32_t w_stage = (uint32_t)L.nt * 128u;             // one [hi|lo] weight tile image
+    const uint32_t w_stage = (uint32_t)L.nt * (L.cat ? 256u : 128u);   // one weight image: a tap ([hi|lo] rows), or in cat mode
+                                                                // a PAIR of taps ([hi_t|hi_t+1] rows, then [lo_t|lo_t+1] rows)
     const int wslots = L.resident ? L.ws : 2 * L.ws;
     uint8_t* A0 = smem;                                         // [2][na] stages
     uint8_t* W0 = A0 + (size_t)2 * L.na * a_buf;                // resident: [ws]; ring: [2][ws]
@@ -114,6 +123,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nkb = a.cin / 32;
     const int per_tile = nkb * a.ntaps;
+    const int npairs = (a.ntaps + 1) >> 1;
+    const int wper = L.cat ? nkb * npairs : per_tile;            // weight images per tile
     const int total_tiles = L.ntiles_m * L.ntiles_n;
     const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
@@ -153,7 +164,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
             const int acc = p + 2 * accs;
             mbar_wait(smem_u32(&acc_empty[acc]), (uint32_t)(((lt >> 1) & 1) ^ 1));
             tc_fence_after();
-            const uint32_t dcol = tmem_base + (uint32_t)(acc * L.nt);
+            const uint32_t dcol = tmem_base + (uint32_t)(acc * L.accw);
             for (int kb = 0; kb < nkb; kb++, lit++) {
                 const int as = lit % L.na;
                 mbar_wait(smem_u32(&a_full[p * TC_MAX_ASTAGES + as]), (uint32_t)((lit / L.na) & 1));
@@ -163,16 +174,27 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                 for (int t = 0; t < a.ntaps; t++, lwit++) {
                     int ws;
                     if (L.resident) {
-                        ws = kb * a.ntaps + t;
+                        ws = L.cat ? kb * npairs + (t >> 1) : kb * a.ntaps + t;
                         if (lt == 0) { mbar_wait(smem_u32(&wf[ws]), 0); tc_fence_after(); }   // loaded once, stays
                     } else {
                         ws = lwit % L.ws;
                         mbar_wait(smem_u32(&wf[ws]), (uint32_t)((lwit / L.ws) & 1));
                         tc_fence_after();
                     }
-                    const uint32_t wimg = smem_u32(Wp + (size_t)ws * w_stage) >> 4;
+                    const uint32_t wimg = (smem_u32(Wp + (size_t)ws * w_stage) >> 4) + (L.cat ? (uint32_t)(t & 1) * 4u : 0u);
                     const uint32_t arow = aimg + (uint32_t)(a.tap_off[t] - a.min_off) * 8u;      // rows * 128 B >> 4
-                    if (elect_one()) {
+                    if (L.cat) {
+                        if (elect_one()) {
+#pragma unroll
+                            for (int ks = 0; ks < 2; ks++) {
+                                const uint64_t dah = desc_hi | (uint64_t)(arow + ks * 2);
+                                const uint64_t dal = desc_hi | (uint64_t)(arow + 4 + ks * 2);
+                                const uint64_t dw = desc_hi | (uint64_t)(wimg + ks * 2);
+                                tc_mma_bf16(dcol, dah, dw, L.idesc2, (kb | t | ks) ? 1u : 0u);   // [hi*hi | hi*lo]
+                                tc_mma_bf16(dcol, dal, dw, L.idesc, 1u);                          // lo*hi -> first nt columns
+                            }
+                        }
+                    } else if (elect_one()) {
 #pragma unroll
                         for (int ks = 0; ks < 2; ks++) {                 // two K = 16 steps inside the 64-B hi half
                             const uint64_t dah = desc_hi | (uint64_t)(arow + ks * 2);
@@ -201,7 +223,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
             if (L.resident) {
                 if (p == 0) {
                     const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wtc);
-                    for (int s = 0; s < per_tile; s++) {
+                    for (int s = 0; s < wper; s++) {
                         mbar_expect_tx(smem_u32(&w_full[s]), w_stage);
                         bulk_g2s(smem_u32(W0 + (size_t)s * w_stage), wsrc + (size_t)s * w_stage, w_stage, smem_u32(&w_full[s]));
                     }
@@ -412,7 +434,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                 mbar_wait(smem_u32(&acc_full[acc]), (uint32_t)((lt >> 1) & 1));
                 tc_fence_after();
                 if (p == 0 && warp == TC_EPI0 && lane == 0) TC_TRACE(a, lt, 5);
-                const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * L.nt);
+                const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * L.accw);
                 for (int h = 0; h < npc; h++) {
                     if (h + 1 < npc) pre(h + 1, mn);
                     float o[16];
@@ -487,7 +509,13 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                 tc_fence_after();
                 if (p == 0 && warp == TC_EPI0 && lane == 0) TC_TRACE(a, lt, 5);
                 float o[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * L.nt), o);
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * L.accw), o);
+                if (L.cat) {                  // second column half: the hi*lo products
+                    float t[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * L.accw + 32), t);
+#pragma unroll
+                    for (int j = 0; j < 32; j++) o[j] += t[j];
+                }
                 tc_fence_before();
                 mbar_arrive(smem_u32(&acc_empty[acc]));
                 if (p == 0 && warp == TC_EPI0 && lane == 0) TC_TRACE(a, lt, 6);
@@ -580,7 +608,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
             if (p == 0 && warp == TC_EPI0 && lane == 0) TC_TRACE(a, lt, 5);
             for (int ch = 0; ch < nch; ch++) {
                 float o[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * L.nt + ch * 32), o);
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * L.accw + ch * 32), o);   // (cat mode: MODE 2 only)
                 if (ch == nch - 1) {          // accumulator fully read: hand it back to its MMA warp
                     tc_fence_before();
                     mbar_arrive(smem_u32(&acc_empty[acc]));
@@ -696,8 +724,7 @@ bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem) {
     if (a.res && (a.ldres & 3)) L.tma_st = 0;
     L.win = (128 + a.span + 7) & ~7;
     if (L.win * 4 > TC_MAXCH * TC_GROUP) return false;
-    L.tmem_cols = 32;
-    while (L.tmem_cols < 4 * L.nt) L.tmem_cols <<= 1;
+    L.cat = 0; L.accw = L.nt; L.idesc2 = 0;
     // kind::f16 instruction descriptor: D fp32 (1<<4), A = B = BF16 (1<<7, 1<<10), K-major both, N>>3, M>>4
     L.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(L.nt >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     L.ntiles_m = (a.rows_q + 127) / 128;
@@ -709,9 +736,16 @@ bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem) {
     const size_t bar_bytes = (2 * TC_MAX_WRING + 6 * TC_MAX_ASTAGES + 12) * 8 + 16 + (L.tma_st ? 4 * TC_OUT_BYTES : 0);
     L.bulk_in = (getenv("SB200_TC_NOBULKIN") == nullptr && a.ldx == 32 && a.cin == 32) ? 1 : 0;
     L.resident = (L.ntiles_n == 1 && per_tile <= TC_MAX_WRING && per_tile * w_stage + 4 * a_buf + bar_bytes <= budget) ? 1 : 0;
-    L.ws = L.resident ? per_tile : (per_tile < 4 ? per_tile : 4);
+    const int wper_cat = (a.cin / 32) * ((a.ntaps + 1) / 2);
+    if (a.wcat && L.tma_st && L.nt <= 64 && L.resident && wper_cat * 2 * w_stage + 4 * a_buf + bar_bytes <= budget && !getenv("SB200_TC_NOCAT")) {
+        L.cat = 1; L.accw = 2 * L.nt;
+        L.idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * L.nt) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    }
+    L.tmem_cols = 32;
+    while (L.tmem_cols < 4 * L.accw) L.tmem_cols <<= 1;
+    L.ws = L.resident ? (L.cat ? wper_cat : per_tile) : (per_tile < 4 ? per_tile : 4);
     if (!L.resident && L.ws < 2) L.ws = 2;
-    auto total = [&]() { return (size_t)2 * L.na * a_buf + (size_t)(L.resident ? L.ws : 2 * L.ws) * w_stage + bar_bytes; };
+    auto total = [&]() { return (size_t)2 * L.na * a_buf + (size_t)(L.resident ? L.ws : 2 * L.ws) * w_stage * (L.cat ? 2 : 1) + bar_bytes; };
     L.na = TC_MAX_ASTAGES;
     { const char* e = getenv("SB200_TC_NA"); if (e) L.na = atoi(e); }     // tuning knob
     while (L.na > 2 && total() > budget) L.na--;
@@ -737,7 +771,7 @@ bool plan_stk(const ConvArgs& a, ConvArgs& v, TcLaunch& L, size_t& smem) {
     if (dil < 1) return false;
     for (int t = 0; t < a.ntaps; t++) if (a.tap_off[t] != a.min_off + t * dil) return false;
     const int slots = 4, ng = (a.ntaps + slots - 1) / slots;
-    L.nt = 128; L.slots = slots; L.dil = dil;
+    L.nt = 128; L.slots = slots; L.dil = dil; L.cat = 0; L.accw = 128; L.idesc2 = 0;
     L.tq = 128 - (slots - 1) * dil;
     if (L.tq < 32) return false;
     v = a;
@@ -814,14 +848,16 @@ void launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     if (!plan(a, L, smem)) { launch_conv_simt(a, st); return; }
     const int tiles = L.ntiles_m * L.ntiles_n;
     const int grid = tiles < tc_num_sms() ? tiles : tc_num_sms();
+    v = a;
+    if (L.cat) v.wtc = a.wcat;
     if (L.tma_st && L.resident && make_out_map(&tm, a.y0 + (size_t)a.orow_add * a.ldy0, a.rows_q, a.ldy0) &&
         (!a.res || make_out_map(&tmr, const_cast<float*>(a.res) + (size_t)a.orow_add * a.ldres, a.rows_q, a.ldres))) {
-        conv_tc_kernel<2><<<grid, TC2_THREADS, smem, st>>>(a, L, tm, tmr);
+        conv_tc_kernel<2><<<grid, TC2_THREADS, smem, st>>>(v, L, tm, tmr);
         g_launch_count++;
         check_launch("conv_tc_tma");
         return;
     }
-    conv_tc_kernel<0><<<grid, TC2_THREADS, smem, st>>>(a, L, tm, tmr);
+    conv_tc_kernel<0><<<grid, TC2_THREADS, smem, st>>>(v, L, tm, tmr);
     g_launch_count++;
     check_launch("conv_tc");
 }
@@ -855,6 +891,43 @@ void conv_tc_build_weights(const float* wt /*[ntaps][cin][ldw]*/, int ldw, int c
                         img[(size_t)n * 64 + (size_t)(((ch + 4) ^ (n & 7)) << 3) + e] = l;
                     }
                 o += (size_t)nt * 64;
+            }
+}
+
+// cat-mode images: [n-tile][K-block][tap pair] images of 2*nt rows x 128 B; row n < nt = [hi of tap 2p : 32 ch |
+// hi of tap 2p+1 : 32 ch], row nt + n = the lo parts, K-major SWIZZLE_128B.  Same total size as the plain images
+// (plus one half-empty image when the tap count is odd).
+size_t conv_tc_cat_weight_floats(int cin, int cout, int ntaps, int nt) {
+    const int ntiles = (cout + nt - 1) / nt;
+    return (size_t)ntiles * (cin / 32) * ((ntaps + 1) / 2) * 2 * nt * 32;
+}
+
+void conv_tc_build_weights_cat(const float* wt /*[ntaps][cin][ldw]*/, int ldw, int cin, int cout, int ntaps, int nt,
+                               float* out) {
+    const int ntiles = (cout + nt - 1) / nt, nkb = cin / 32, npairs = (ntaps + 1) / 2;
+    uint16_t* o16 = reinterpret_cast<uint16_t*>(out);
+    memset(o16, 0, conv_tc_cat_weight_floats(cin, cout, ntaps, nt) * 4);
+    size_t o = 0;
+    for (int j = 0; j < ntiles; j++)
+        for (int kb = 0; kb < nkb; kb++)
+            for (int pr = 0; pr < npairs; pr++) {
+                uint16_t* img = o16 + o;
+                for (int h = 0; h < 2; h++) {
+                    const int t = 2 * pr + h;
+                    if (t >= ntaps) continue;
+                    for (int n = 0; n < nt; n++)
+                        for (int c = 0; c < 32; c++) {
+                            const int col = j * nt + n;
+                            const float v = col < cout ? wt[((size_t)t * cin + kb * 32 + c) * ldw + col] : 0.f;
+                            const uint16_t hi = bf16_rn_host(v);
+                            const uint16_t lo = bf16_rn_host(v - bf16_to_float_host(hi));
+                            const int ch = h * 4 + (c >> 3), e = c & 7;
+                            const int rl = nt + n;
+                            img[(size_t)n * 64 + (size_t)((ch ^ (n & 7)) << 3) + e] = hi;
+                            img[(size_t)rl * 64 + (size_t)((ch ^ (rl & 7)) << 3) + e] = lo;
+                        }
+                }
+                o += (size_t)2 * nt * 64;
             }
 }
 

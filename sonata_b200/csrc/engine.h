@@ -50,6 +50,7 @@ struct ConvW {
     float* bias = nullptr;
     float* wtc = nullptr; int tc_nt = 0;     // tcgen05 hi/lo swizzled weight images
     float* wts = nullptr;                    // tap-stacked images for the 32-channel layers (conv_ts.cu)
+    float* wcat = nullptr;                   // hi/lo-stacked tap-pair images (conv_tc.cu cat mode), column tiles <= 64
     int cin = 0, cout = 0, ldw = 0, ntaps = 0;
     int tap_off[SB_MAX_TAPS] = {0};
     int min_off = 0, span = 0;

@@ -87,6 +87,11 @@ void add_tc_images(Uploader& U, ConvW& c, const std::vector<float>& wt) {
     conv_tc_build_weights(wt.data(), c.ldw, c.cin, c.cout, c.ntaps, nt, img.data());
     c.wtc = U.up(img);
     c.tc_nt = nt;
+    if (nt <= 64) {
+        std::vector<float> cat(conv_tc_cat_weight_floats(c.cin, c.cout, c.ntaps, nt));
+        conv_tc_build_weights_cat(wt.data(), c.ldw, c.cin, c.cout, c.ntaps, nt, cat.data());
+        c.wcat = U.up(cat);
+    }
     if (c.cin == 32 && c.cout == 32 && c.ntaps >= 3 && c.ntaps <= 16) {   // stacked-tap images (conv_tc.cu STK mode)
         std::vector<float> ts(conv_ts_weight_floats(c.ntaps));
         conv_ts_build_weights(wt.data(), c.ldw, c.ntaps, ts.data());
