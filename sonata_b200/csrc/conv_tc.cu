@@ -57,6 +57,8 @@ struct TcLaunch {
     int ntiles_m, ntiles_n;
     uint32_t idesc;
     int bulk_in;     // input rows are contiguous 128-B rows (ldx == 32): a window is ONE block -> one TMA bulk copy
+    int tma_in;      // the window of a K-block arrives by ONE TMA tensor load (box 32 channels x win rows; rows outside
+                     // the array are zero-filled by the engine): no LDGSTS traffic through the LSU / L1TEX pipe
     // "stacked" mode (STK): the N = 128 columns of a tile are 128/cout TAPS x cout channels (see the epilogue)
     int tq;          // output rows per tile (128 normally; 128 - (slots-1)*dil when stacked)
     int slots;       // taps stacked along N
@@ -97,7 +99,8 @@ constexpr int TC_OUT_BYTES = 128 * 128;  // MODE 2: one staged output tile (128 
 template <int MODE>
 __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs a, const TcLaunch L,
                                                                   const __grid_constant__ CUtensorMap tm_out,
-                                                                  const __grid_constant__ CUtensorMap tm_res) {
+                                                                  const __grid_constant__ CUtensorMap tm_res,
+                                                                  const __grid_constant__ CUtensorMap tm_x) {
     constexpr bool STK = MODE == 1;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -297,7 +300,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
             if (p == 0 && gt == 0 && kb == 0) TC_TRACE(a, lt, 0);
             const uint32_t img = smem_u32(Ap + (size_t)as * a_buf);
             const float* xk = a.x + kb * 32;
-            if (L.bulk_in && rbase >= 0 && rbase + L.win <= a.rows_in) {
+            if (L.tma_in) {
+                if (gt == 0) {
+                    mbar_expect_tx(smem_u32(&raw_full[p * TC_MAX_ASTAGES + as]), a_buf);
+                    tma_load_2d(img, &tm_x, smem_u32(&raw_full[p * TC_MAX_ASTAGES + as]), kb * 32, rbase);
+                }
+            } else if (L.bulk_in && rbase >= 0 && rbase + L.win <= a.rows_in) {
                 // contiguous 32-channel rows: the whole window is one block -> one TMA bulk copy (keeps the window
                 // traffic out of the LSU / L1 miss queue; measured +1.4 %)
                 if (gt == 0) {
@@ -333,7 +341,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                 const int lt_ = j / nkb;
                 const int tg_ = (int)blockIdx.x + (p + 2 * lt_) * (int)gridDim.x;
                 const int rb_ = (tg_ / L.ntiles_n) * L.tq + a.min_off;
-                if (L.bulk_in && rb_ >= 0 && rb_ + L.win <= a.rows_in) {
+                if (L.tma_in || (L.bulk_in && rb_ >= 0 && rb_ + L.win <= a.rows_in)) {
                     const int as_ = j % L.na;
                     mbar_wait(smem_u32(&raw_full[p * TC_MAX_ASTAGES + as_]), (rawpar >> as_) & 1u);
                     rawpar ^= 1u << as_;
@@ -704,6 +712,18 @@ bool make_out_map(CUtensorMap* tm, float* base, int rows, int ld) {
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// [rows][cin] fp32 view of a conv input: boxes of 32 channels x win rows, linear (unswizzled) in shared memory --
+// exactly the raw window image the producers convert in place
+bool make_in_map(CUtensorMap* tm, const float* base, int rows, int cin, int ld, int win) {
+    const cuuint64_t dims[2] = {(cuuint64_t)cin, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {32, (cuuint32_t)win};
+    const cuuint32_t estr[2] = {1, 1};
+    return tensor_map_encoder()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // 256-bit epilogue accesses need 32-byte aligned rows and column blocks for every operand that is used
 bool epi_v8_ok(const ConvArgs& a) {
     if (getenv("SB200_TC_NOV8")) return false;
@@ -735,6 +755,8 @@ bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem) {
     const size_t budget = 225 * 1024 - 2048;
     const size_t bar_bytes = (2 * TC_MAX_WRING + 6 * TC_MAX_ASTAGES + 12) * 8 + 16 + (L.tma_st ? 4 * TC_OUT_BYTES : 0);
     L.bulk_in = (getenv("SB200_TC_NOBULKIN") == nullptr && a.ldx == 32 && a.cin == 32) ? 1 : 0;
+    L.tma_in = (tensor_map_encoder() != nullptr && L.win <= 256 && (a.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0 &&
+                !getenv("SB200_TC_NOTMAIN")) ? 1 : 0;
     L.resident = (L.ntiles_n == 1 && per_tile <= TC_MAX_WRING && per_tile * w_stage + 4 * a_buf + bar_bytes <= budget) ? 1 : 0;
     const int wper_cat = (a.cin / 32) * ((a.ntaps + 1) / 2);
     if (a.wcat && L.tma_st && L.nt <= 64 && L.resident && wper_cat * 2 * w_stage + 4 * a_buf + bar_bytes <= budget && !getenv("SB200_TC_NOCAT")) {
@@ -789,6 +811,7 @@ bool plan_stk(const ConvArgs& a, ConvArgs& v, TcLaunch& L, size_t& smem) {
     const size_t budget = 225 * 1024 - 2048;
     const size_t bar_bytes = (2 * TC_MAX_WRING + 6 * TC_MAX_ASTAGES + 12) * 8 + 16;
     L.bulk_in = (getenv("SB200_TC_NOBULKIN") == nullptr && a.ldx == 32) ? 1 : 0;
+    L.tma_in = 0;
     L.resident = 1; L.ws = ng;
     L.na = TC_MAX_ASTAGES;
     { const char* e = getenv("SB200_TC_NA"); if (e) L.na = atoi(e); }
@@ -835,12 +858,13 @@ void launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     }
     TcLaunch L; size_t smem;
     ConvArgs v;
-    CUtensorMap tm, tmr;
+    CUtensorMap tm, tmr, tmx;
     memset(&tm, 0, sizeof(tm));
     memset(&tmr, 0, sizeof(tmr));
+    memset(&tmx, 0, sizeof(tmx));
     if (plan_stk(a, v, L, smem)) {                                    // experimental: four taps per MMA (opt-in)
         const int grid = L.ntiles_m < tc_num_sms() ? L.ntiles_m : tc_num_sms();
-        conv_tc_kernel<1><<<grid, TC2_THREADS, smem, st>>>(v, L, tm, tmr);
+        conv_tc_kernel<1><<<grid, TC2_THREADS, smem, st>>>(v, L, tm, tmr, tmx);
         g_launch_count++;
         check_launch("conv_tc_stk");
         return;
@@ -850,14 +874,15 @@ void launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     const int grid = tiles < tc_num_sms() ? tiles : tc_num_sms();
     v = a;
     if (L.cat) v.wtc = a.wcat;
+    if (L.tma_in && !make_in_map(&tmx, a.x, a.rows_in, a.cin, a.ldx, L.win)) L.tma_in = 0;
     if (L.tma_st && L.resident && make_out_map(&tm, a.y0 + (size_t)a.orow_add * a.ldy0, a.rows_q, a.ldy0) &&
         (!a.res || make_out_map(&tmr, const_cast<float*>(a.res) + (size_t)a.orow_add * a.ldres, a.rows_q, a.ldres))) {
-        conv_tc_kernel<2><<<grid, TC2_THREADS, smem, st>>>(v, L, tm, tmr);
+        conv_tc_kernel<2><<<grid, TC2_THREADS, smem, st>>>(v, L, tm, tmr, tmx);
         g_launch_count++;
         check_launch("conv_tc_tma");
         return;
     }
-    conv_tc_kernel<0><<<grid, TC2_THREADS, smem, st>>>(v, L, tm, tmr);
+    conv_tc_kernel<0><<<grid, TC2_THREADS, smem, st>>>(v, L, tm, tmr, tmx);
     g_launch_count++;
     check_launch("conv_tc");
 }
