@@ -345,7 +345,7 @@ def main():
             "share_of_step": mrf_ms / all_ms if all_ms else None,
             "achieved_tflops": mrf_flops / (mrf_ms * 1e-3) / 1e12 if mrf_ms else 0.0,
             "tensor_peak_tflops": peaks["bf16_tflops_sustained"],
-            "note": "algorithmic bytes = each conv's input + residual + output read/written once (fp32) + weights; "
+            "note": "algorithmic bytes = each conv's input + output (+ the residual when it is NOT the conv input, + the accumulated buffer when read-modify-written) once, fp32, + weights; "
                     "FLOPs at 2/MAC over valid rows",
         }
         regions = {k: {"ms_per_step": v["ms"] / args.steps, "tflops": v["flops"] / max(v["ms"], 1e-9) / 1e9,

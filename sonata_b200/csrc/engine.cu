@@ -164,7 +164,7 @@ struct Runner {
         const double vr = (double)lin.valid_rows;
         const int cout_w = (o.act == ACT_GATE) ? w.cout / 2 : w.cout;
         count(2.0 * vr * w.cin * w.cout * w.ntaps,
-              4.0 * (vr * (w.cin + cout_w + (o.res ? w.cout : 0) + ((o.acc0 | o.acc1) ? w.cout : 0)) +
+              4.0 * (vr * (w.cin + cout_w + ((o.res && o.res != x) ? w.cout : 0) + ((o.acc0 | o.acc1) ? w.cout : 0)) +
                      (double)w.ntaps * w.cin * w.cout));
     }
 
