@@ -27,6 +27,10 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
 }
+__device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, bool ok) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(ok ? 16u : 0u));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
 
@@ -45,8 +49,12 @@ __global__ void __launch_bounds__(256, 2) conv_simt_kernel(const ConvArgs a) {
 
     extern __shared__ __align__(16) float smem[];
     const int win = BM + a.span;
-    float* As = smem;
-    float* Bs = smem + win * AS_STRIDE;
+    // With no leaky-ReLU prologue (in_slope == 1: encoder / duration-predictor GEMMs) the window of the NEXT
+    // 32-channel chunk is prefetched with cp.async into a second buffer while the current chunk is computed; a
+    // synchronous load exposed a full memory latency per chunk (every iteration for the k = 1 projections).
+    const bool pfa = a.in_slope == 1.f;
+    float* As0 = smem;
+    float* Bs = smem + 2 * win * AS_STRIDE;
 
     const int tid = threadIdx.x;
     const int tx = tid % TX, ty = tid / TX;
@@ -74,11 +82,24 @@ __global__ void __launch_bounds__(256, 2) conv_simt_kernel(const ConvArgs a) {
         cp_async_commit();
     };
 
+    auto issue_a = [&](int chunk) {           // async window load of `chunk` (joins the next committed group)
+        float* dstA = As0 + (chunk & 1) * (win * AS_STRIDE);
+        const int c0 = chunk * BK;
+        const int rbase = q0 + a.min_off;
+        for (int idx = tid; idx < win * 8; idx += 256) {
+            const int r = idx >> 3, c4 = idx & 7;
+            const int gr = rbase + r;
+            const bool ok = gr >= 0 && gr < a.rows_in;
+            cp_async16_zfill(dstA + r * AS_STRIDE + c4 * 4, ok ? a.x + (size_t)gr * a.ldx + c0 + c4 * 4 : a.x, ok);
+        }
+    };
+    if (pfa) issue_a(0);
     issue_b(0, 0);
     for (int it = 0; it < nit; it++) {
         const int chunk = it / a.ntaps, t = it - chunk * a.ntaps;
         const int buf = it & 1;
-        if (t == 0) {
+        float* As = As0 + (pfa ? (chunk & 1) * (win * AS_STRIDE) : 0);
+        if (t == 0 && !pfa) {
             __syncthreads();   // everyone is done reading the previous window
             const int c0 = chunk * BK;
             const int rbase = q0 + a.min_off;
@@ -98,7 +119,10 @@ __global__ void __launch_bounds__(256, 2) conv_simt_kernel(const ConvArgs a) {
         }
         cp_async_wait_all();
         __syncthreads();       // weights(it) + window visible; compute(it-1) finished everywhere
-        if (it + 1 < nit) issue_b(it + 1, buf ^ 1);
+        if (it + 1 < nit) {
+            if (pfa && t + 1 == a.ntaps) issue_a(chunk + 1);     // buffer (chunk+1)&1 was last read in chunk-1: all done
+            issue_b(it + 1, buf ^ 1);
+        }
 
         const float* Ab = As + (ty + a.tap_off[t] - a.min_off) * AS_STRIDE;
         const float* Bb = Bs + buf * (BK * BN) + tx * VW;
@@ -190,7 +214,7 @@ void launch_cfg(const ConvArgs& a, cudaStream_t st) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         attr_done = true;
     }
-    const size_t smem = ((size_t)(BM + a.span) * AS_STRIDE + 2 * BK * BN) * sizeof(float);
+    const size_t smem = ((size_t)2 * (BM + a.span) * AS_STRIDE + 2 * BK * BN) * sizeof(float);
     dim3 grid((a.rows_q + BM - 1) / BM, a.ldw / BN);
     kern<<<grid, 256, smem, st>>>(a);
     g_launch_count++;
