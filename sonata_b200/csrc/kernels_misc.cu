@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(2 * D) attention_kernel(const float* __restric
     float* S = Qs + ATT_QT * D;                   // [QT][tpad]
     float* qE = S + ATT_QT * tpad;                // [QT][nrel]
     float* inv = qE + ATT_QT * nrel;              // [QT]
-    float* Osum = inv + ATT_QT;                   // [2][QT][D] partial outputs of the two j-halves
+    float* Osum = inv + ATT_QT;                   // [4][QT][D] partial outputs of the four key-range quarters
 
     const float* qbase = qkv + (size_t)sg.off * ldq + head * D;
     const float* kbase = qbase + H;
@@ -172,26 +172,43 @@ __global__ void __launch_bounds__(2 * D) attention_kernel(const float* __restric
         for (int c = 0; c < D; c++) s = fmaf(Qs[i * D + c], relk[d * D + c], s);
         qE[idx] = s;
     }
-    // scores: one key per thread per pass
-    for (int j = tid; j < T; j += NT) {
-        float acc[ATT_QT];
+    // scores: KPT keys per thread, all ATT_QT queries in registers.  Every Q value is a broadcast LDS that feeds one
+    // FMA per key held by the thread: with one key per thread the phase issued one LDS.128 per four FMAs and was
+    // bound by the load/store unit, not by the FP32 pipe.
+    constexpr int KPT = 3;
+    for (int j0 = tid * KPT; j0 < T; j0 += NT * KPT) {
+        float acc[KPT][ATT_QT];
 #pragma unroll
-        for (int i = 0; i < ATT_QT; i++) acc[i] = 0.f;
-        const float4* kr = reinterpret_cast<const float4*>(kbase + (size_t)j * ldq);
+        for (int k = 0; k < KPT; k++)
+#pragma unroll
+            for (int i = 0; i < ATT_QT; i++) acc[k][i] = 0.f;
+        const float4* kr[KPT];
+#pragma unroll
+        for (int k = 0; k < KPT; k++)
+            kr[k] = reinterpret_cast<const float4*>(kbase + (size_t)min(j0 + k, T - 1) * ldq);
 #pragma unroll 2
         for (int c4 = 0; c4 < D / 4; c4++) {
-            const float4 kv = kr[c4];
+            float4 kv[KPT];
+#pragma unroll
+            for (int k = 0; k < KPT; k++) kv[k] = kr[k][c4];
 #pragma unroll
             for (int i = 0; i < ATT_QT; i++) {
                 const float4 qv = *reinterpret_cast<const float4*>(Qs + i * D + c4 * 4);
-                acc[i] = fmaf(qv.x, kv.x, acc[i]);
-                acc[i] = fmaf(qv.y, kv.y, acc[i]);
-                acc[i] = fmaf(qv.z, kv.z, acc[i]);
-                acc[i] = fmaf(qv.w, kv.w, acc[i]);
+#pragma unroll
+                for (int k = 0; k < KPT; k++) {
+                    acc[k][i] = fmaf(qv.x, kv[k].x, acc[k][i]);
+                    acc[k][i] = fmaf(qv.y, kv[k].y, acc[k][i]);
+                    acc[k][i] = fmaf(qv.z, kv[k].z, acc[k][i]);
+                    acc[k][i] = fmaf(qv.w, kv[k].w, acc[k][i]);
+                }
             }
         }
 #pragma unroll
-        for (int i = 0; i < ATT_QT; i++) S[i * tpad + j] = acc[i];
+        for (int k = 0; k < KPT; k++)
+            if (j0 + k < T) {
+#pragma unroll
+                for (int i = 0; i < ATT_QT; i++) S[i * tpad + j0 + k] = acc[k][i];
+            }
     }
     __syncthreads();
     // add relative logits, softmax (one warp per query row, round-robin)
@@ -219,38 +236,40 @@ __global__ void __launch_bounds__(2 * D) attention_kernel(const float* __restric
         S[i * tpad + j] = 0.f;
     }
     __syncthreads();
-    // P.V : thread = (half, channel)
+    // P.V : thread = (quarter of the key range, channel PAIR): two channels per thread halve the broadcast LDS of the
+    // probabilities per FMA (same load/store-unit argument as in the score phase)
     {
-        const int half = tid / D, c = tid % D;
-        float acc[ATT_QT];
+        const int part = tid / (D / 2), cp = tid % (D / 2);
+        float acc[ATT_QT][2];
 #pragma unroll
-        for (int i = 0; i < ATT_QT; i++) acc[i] = 0.f;
+        for (int i = 0; i < ATT_QT; i++) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
         const int nj4 = tpad / 4;
-        for (int j4 = half; j4 < nj4; j4 += 2) {
-            float vv[4];
+        for (int j4 = part; j4 < nj4; j4 += 4) {
+            float2 vv[4];
 #pragma unroll
             for (int e = 0; e < 4; e++) {
                 const int j = j4 * 4 + e;
-                vv[e] = j < T ? vbase[(size_t)j * ldq + c] : 0.f;
+                vv[e] = j < T ? *reinterpret_cast<const float2*>(vbase + (size_t)j * ldq + cp * 2) : make_float2(0.f, 0.f);
             }
 #pragma unroll
             for (int i = 0; i < ATT_QT; i++) {
                 const float4 p = *reinterpret_cast<const float4*>(S + i * tpad + j4 * 4);
-                acc[i] = fmaf(p.x, vv[0], acc[i]);
-                acc[i] = fmaf(p.y, vv[1], acc[i]);
-                acc[i] = fmaf(p.z, vv[2], acc[i]);
-                acc[i] = fmaf(p.w, vv[3], acc[i]);
+                acc[i][0] = fmaf(p.x, vv[0].x, acc[i][0]); acc[i][1] = fmaf(p.x, vv[0].y, acc[i][1]);
+                acc[i][0] = fmaf(p.y, vv[1].x, acc[i][0]); acc[i][1] = fmaf(p.y, vv[1].y, acc[i][1]);
+                acc[i][0] = fmaf(p.z, vv[2].x, acc[i][0]); acc[i][1] = fmaf(p.z, vv[2].y, acc[i][1]);
+                acc[i][0] = fmaf(p.w, vv[3].x, acc[i][0]); acc[i][1] = fmaf(p.w, vv[3].y, acc[i][1]);
             }
         }
 #pragma unroll
-        for (int i = 0; i < ATT_QT; i++) Osum[(half * ATT_QT + i) * D + c] = acc[i];
+        for (int i = 0; i < ATT_QT; i++)
+            *reinterpret_cast<float2*>(Osum + (part * ATT_QT + i) * D + cp * 2) = make_float2(acc[i][0], acc[i][1]);
     }
     __syncthreads();
     for (int idx = tid; idx < ATT_QT * D; idx += NT) {
         const int i = idx / D, c = idx % D;
         const int ia = i0 + i;
         if (ia >= T) continue;
-        float o = Osum[i * D + c] + Osum[(ATT_QT + i) * D + c];
+        float o = (Osum[i * D + c] + Osum[(ATT_QT + i) * D + c]) + (Osum[(2 * ATT_QT + i) * D + c] + Osum[(3 * ATT_QT + i) * D + c]);
         for (int d = 0; d < nrel; d++) {
             const int j = ia + d - window;
             if (j >= 0 && j < T) o = fmaf(S[i * tpad + j], relv[d * D + c], o);
@@ -553,7 +572,7 @@ static int att_tpad(int max_len) { return (max_len + 3) & ~3; }
 
 size_t attention_smem_bytes(int max_len, int D) {
     const int tpad = att_tpad(max_len);
-    return sizeof(float) * ((size_t)ATT_QT * D + (size_t)ATT_QT * tpad + ATT_QT * 32 + ATT_QT + 2 * ATT_QT * D);
+    return sizeof(float) * ((size_t)ATT_QT * D + (size_t)ATT_QT * tpad + ATT_QT * 32 + ATT_QT + 4 * ATT_QT * D);
 }
 
 void launch_attention(const float* qkv, int ldq, const float* relk, const float* relv, int window, float* out,
