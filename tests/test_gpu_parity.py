@@ -90,6 +90,19 @@ def test_conv_kernels_against_torch(backend, lib_built):
         assert err < 1e-4, (c, err)
 
 
+@pytest.mark.parametrize("knob", ["SB200_TS", "SB200_STK", "SB200_TC_NOTMAST", "SB200_TC_NOTMAIN", "SB200_TC_NOV8"])
+def test_conv_kernel_variants_stay_correct(knob, lib_built):
+    """The opt-in formulations (tap-stacked transposed kernel, stacked-tap mode) and the fallbacks of the default path
+    (no TMA-staged epilogue, cp.async window loads, 128-bit epilogue accesses) implement the same ConvArgs contract.
+    The planner reads the knobs from the environment, so each variant runs in its own process."""
+    import subprocess
+    env = dict(os.environ, **{knob: "1"})
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "conv_unit.py")
+    r = subprocess.run([sys.executable, tool, "1", "0,1,2,3,12,17,18,19,20,21,22,23,25,26"], env=env, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_batched_equals_sequential(models):
     """speak_batch is a sequential B=1 loop in the reference (piper/src/lib.rs:433-435): the packed
     batched pass must give each utterance the result it gets alone."""
