@@ -128,6 +128,11 @@ int32_t sb200_job_run(sb200_job* job, float* d_out, size_t d_out_capacity, float
 int32_t sb200_job_fetch(sb200_job* job, sb200_audio* outs, sb200_error* err);
 size_t sb200_job_batch(const sb200_job* job);
 /* per-utterance results available after run: frames (T_y), samples (256*T_y), offset into d_out */
+/* Peak-normalised 16-bit PCM of every utterance of a finished job, converted on the device (half the device->host
+ * bytes).  Mirrors AudioSamples::to_i16_vec / as_wave_bytes (crates/audio/ops/src/samples.rs:51-78) bit for bit.
+ * outs[b] receives a malloc'ed buffer of lens[b] samples: free with sb200_i16_free. */
+int32_t sb200_job_fetch_i16(sb200_job* job, int16_t** outs, size_t* lens, sb200_error* err);
+void sb200_i16_free(int16_t* p);
 int32_t sb200_job_lengths(const sb200_job* job, int64_t* frames, int64_t* samples, int64_t* out_offsets);
 void sb200_job_free(sb200_job* job);
 

@@ -70,6 +70,8 @@ SIGNATURES = {
     "sb200_job_set_debug": (C.c_int32, [_P, C.c_int32]),
     "sb200_job_run": (C.c_int32, [_P, C.c_void_p, C.c_size_t, C.POINTER(C.c_float), _ERR]),
     "sb200_job_fetch": (C.c_int32, [_P, C.POINTER(sb200_audio), _ERR]),
+    "sb200_job_fetch_i16": (C.c_int32, [_P, C.POINTER(C.POINTER(C.c_int16)), C.POINTER(C.c_size_t), _ERR]),
+    "sb200_i16_free": (None, [C.POINTER(C.c_int16)]),
     "sb200_job_batch": (C.c_size_t, [_P]),
     "sb200_job_lengths": (C.c_int32, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "sb200_job_free": (None, [_P]),

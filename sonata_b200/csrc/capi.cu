@@ -226,6 +226,36 @@ int32_t sb200_job_run(sb200_job* job, float* d_out, size_t cap, float* device_ms
 int32_t sb200_job_fetch(sb200_job* job, sb200_audio* outs, sb200_error* err) {
     return guarded(err, [&] { fetch_audio(*job->j, outs, job->j->last_ms); });
 }
+int32_t sb200_job_fetch_i16(sb200_job* job, int16_t** outs, size_t* lens, sb200_error* err) {
+    return guarded(err, [&] {
+        Job& j = *job->j;
+        if (!j.ran || j.encode_only) throw Error(19, "job has not produced audio");
+        Voice& v = *j.v;
+        SB_CUDA(cudaSetDevice(v.device));
+        const int hop = v.a.hop();
+        long long mx = 0;
+        for (size_t b = 0; b < j.B; b++) mx = std::max<long long>(mx, (long long)j.y_len[b] * hop);
+        short* d_i16 = nullptr; unsigned* d_max = nullptr;
+        SB_CUDA(cudaMallocAsync(&d_i16, (size_t)j.total_samples * 2 + 16, j.ctx->stream));
+        SB_CUDA(cudaMallocAsync(&d_max, sizeof(unsigned) * j.B, j.ctx->stream));
+        launch_i16(j.d_wav, j.d_fsegs, (int)j.B, hop, mx, d_max, d_i16, j.ctx->stream);
+        PinnedBlock* blk = pin_acquire((size_t)j.total_samples * 2 + 16);
+        cudaError_t e = cudaMemcpyAsync(blk->base, d_i16, (size_t)j.total_samples * 2, cudaMemcpyDeviceToHost, j.ctx->stream);
+        cudaFreeAsync(d_i16, j.ctx->stream);
+        cudaFreeAsync(d_max, j.ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(j.ctx->stream);
+        if (e != cudaSuccess) { pin_release(blk); throw Error(19, std::string("CUDA error: ") + cudaGetErrorString(e)); }
+        const int16_t* h = reinterpret_cast<const int16_t*>(blk->base);
+        for (size_t b = 0; b < j.B; b++) {
+            const size_t n = (size_t)j.y_len[b] * hop;
+            outs[b] = (int16_t*)malloc(n * 2 + 2);
+            memcpy(outs[b], h + j.fsegs[b].out_off, n * 2);
+            lens[b] = n;
+        }
+        pin_release(blk);
+    });
+}
+void sb200_i16_free(int16_t* p) { free(p); }
 size_t sb200_job_batch(const sb200_job* job) { return job->j->B; }
 int32_t sb200_job_lengths(const sb200_job* job, int64_t* frames, int64_t* samples, int64_t* out_offsets) {
     const Job& j = *job->j;

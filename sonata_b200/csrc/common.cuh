@@ -97,6 +97,9 @@ void launch_expand(const float* stats, int ldst, int I, const int* cum, const fl
 // wav = tanh(conv_k7(lrelu_{0.01}(x)))  ->  compact per-segment output
 void launch_conv_post(const float* x, int C, const float* w /*[7][C]*/, float* wav, const FrameSeg* fsegs,
                       const int* ftile_seg, int U, RowMap map, cudaStream_t st);
+// per-utterance peak-normalised f32 -> i16 (audio-ops `to_i16_vec`), out indexed like wav
+void launch_i16(const float* wav, const FrameSeg* fsegs, int nseg, int hop, long long max_samples, unsigned* maxbits,
+                short* out, cudaStream_t st);
 void launch_randn(float* out, long long n, unsigned long long seed, unsigned long long stream_id, cudaStream_t st);
 void launch_scale_copy2(const float* eps, float s, float* z, RowMap map, cudaStream_t st);   // z[r][0..1] = eps*s
 void launch_fill_zero(float* p, long long n, cudaStream_t st);

@@ -489,6 +489,37 @@ __global__ void __launch_bounds__(256) conv_post_kernel(const float* __restrict_
     wav[fs.out_off + (long long)(r - (long long)fs.off * U)] = tanhf(acc);
 }
 
+// ------------------------------------------------------------------ f32 -> i16 with per-utterance peak normalisation
+// crates/audio/ops/src/samples.rs:51-75 (`to_i16_vec`): scale = 32767 / max(|x|_max, f32::EPSILON);
+// y = trunc(clamp(x * scale, -32768, 32767)).  Bit-exact with the host version (same fp32 operations in the same
+// order); halves the device->host bytes of a synthesis result.
+__global__ void i16_absmax_kernel(const float* __restrict__ wav, const FrameSeg* __restrict__ fsegs, int hop,
+                                  unsigned* __restrict__ maxbits) {
+    const FrameSeg fs = fsegs[blockIdx.y];
+    const long long n = (long long)fs.len * hop;
+    const float* x = wav + fs.out_off;
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(x[i]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(maxbits + blockIdx.y, __float_as_uint(m));   // non-negative floats
+                                                                                                  // order like their bits
+}
+
+__global__ void i16_convert_kernel(const float* __restrict__ wav, const FrameSeg* __restrict__ fsegs, int hop,
+                                   const unsigned* __restrict__ maxbits, short* __restrict__ out) {
+    const FrameSeg fs = fsegs[blockIdx.y];
+    const long long n = (long long)fs.len * hop;
+    const float* x = wav + fs.out_off;
+    short* y = out + fs.out_off;
+    const float amax = fmaxf(__uint_as_float(maxbits[blockIdx.y]), 1.1920928955078125e-07f);
+    const float scale = __fdiv_rn(32767.0f, amax);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = fminf(fmaxf(__fmul_rn(x[i], scale), -32768.0f), 32767.0f);
+        y[i] = (short)(int)v;                      // truncating cast
+    }
+}
+
 // ------------------------------------------------------------------ Philox4x32-10 -> N(0,1)
 __device__ __forceinline__ void philox_round(unsigned& c0, unsigned& c1, unsigned& c2, unsigned& c3, unsigned k0,
                                              unsigned k1) {
@@ -634,6 +665,19 @@ void launch_conv_post(const float* x, int C, const float* w, float* wav, const F
         default: break;
     }
     g_launch_count++;
+}
+
+void launch_i16(const float* wav, const FrameSeg* fsegs, int nseg, int hop, long long max_samples, unsigned* maxbits,
+                short* out, cudaStream_t st) {
+    if (nseg <= 0) return;
+    cudaMemsetAsync(maxbits, 0, sizeof(unsigned) * nseg, st);
+    int bx = (int)((max_samples + 256 * 8 - 1) / (256 * 8));
+    if (bx < 1) bx = 1;
+    if (bx > 1024) bx = 1024;
+    dim3 grid(bx, nseg);
+    i16_absmax_kernel<<<grid, 256, 0, st>>>(wav, fsegs, hop, maxbits);
+    i16_convert_kernel<<<grid, 256, 0, st>>>(wav, fsegs, hop, maxbits, out);
+    g_launch_count += 2;
 }
 
 void launch_randn(float* out, long long n, unsigned long long seed, unsigned long long stream_id, cudaStream_t st) {

@@ -63,6 +63,20 @@ class SynthesisJob:
         _check(self._lib.sb200_job_fetch(self._h, outs, C.byref(err)), err)
         return [_take_audio(outs[i]) for i in range(self.batch)]
 
+    def fetch_i16(self) -> List[np.ndarray]:
+        """Per-utterance peak-normalised 16-bit PCM, converted on the device: bit-identical to
+        `Audio.samples.to_i16_vec()` (audio/ops/src/samples.rs:51-75) at half the device->host bytes."""
+        outs = (C.POINTER(C.c_int16) * self.batch)()
+        lens = (C.c_size_t * self.batch)()
+        err = N.sb200_error()
+        _check(self._lib.sb200_job_fetch_i16(self._h, outs, lens, C.byref(err)), err)
+        res = []
+        for i in range(self.batch):
+            n = int(lens[i])
+            res.append(np.ctypeslib.as_array(outs[i], shape=(n,)).copy() if n else np.zeros(0, dtype=np.int16))
+            self._lib.sb200_i16_free(outs[i])
+        return res
+
     def lengths(self):
         f = (C.c_int64 * self.batch)()
         s = (C.c_int64 * self.batch)()

@@ -103,6 +103,23 @@ def test_conv_kernel_variants_stay_correct(knob, lib_built):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_device_i16_matches_host_to_i16_vec(models):
+    """the 16-bit PCM conversion (`to_i16_vec`: per-buffer peak normalisation, clamp, truncating cast,
+    audio/ops/src/samples.rs:51-75) done on the device is bit-identical to the host mirror of the reference."""
+    m = models("medium"); _det(m)
+    batches = [workload.synthetic_ids(n, utt=70 + i) for i, n in enumerate((21, 5, 40))]
+    job = SynthesisJob(m, batches)
+    job.run()
+    f32 = job.fetch()
+    i16 = job.fetch_i16()
+    assert len(i16) == len(f32)
+    for a, q in zip(f32, i16):
+        ref = a.samples.to_i16_vec()
+        assert q.dtype == np.int16 and q.shape == ref.shape
+        assert np.array_equal(q, ref)
+        assert int(np.abs(q.astype(np.int32)).max()) >= 32766       # peak-normalised
+
+
 def test_batched_equals_sequential(models):
     """speak_batch is a sequential B=1 loop in the reference (piper/src/lib.rs:433-435): the packed
     batched pass must give each utterance the result it gets alone."""
