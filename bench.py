@@ -172,7 +172,8 @@ def main():
     cfg_desc = {"workload": f"{args.workload}: synthetic-{quality} (en_US-lessac-{quality} architecture), "
                             f"{B} x {NPH}-phoneme utterances per GPU, scales [0.667,1,0.8]",
                 "quality": quality, "batch_per_gpu": B, "phonemes": NPH, "ids_per_utt": 2 * NPH + 2,
-                "l2": "working set (>5 GB of activations per step) far exceeds the 126 MB L2"}
+                "l2": "working set (>5 GB of activations per step) far exceeds the 126 MB L2",
+                "parallelism": f"dp{world}: independent utterance shards, one process per GPU, no data-path collective"}
     cores = os.cpu_count() or 1
 
     # ------------------------------------------------------------------ reference arm (CPU)
@@ -201,6 +202,11 @@ def main():
         return
 
     # ------------------------------------------------------------------ our arm
+    # stdout must carry exactly ONE line (the JSON): native libraries (NCCL's version banner, for one) write to file
+    # descriptor 1 directly, so fd 1 points at stderr until the line is printed
+    sys.stdout.flush()
+    _stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import sonata_b200
@@ -225,6 +231,10 @@ def main():
     total_utts = B * world
     all_batches = [workload.synthetic_ids(NPH, utt=u) for u in range(total_utts)]
     ids_per_step = sum(len(b) for b in all_batches)
+    # this rank's shard: the same LPT partition `shard.scatter_ids` computes, evaluated locally (it is a pure function
+    # of the id counts), so the timed passes need no collective -- utterances are independent
+    my_idx = shard.lpt_partition([len(b) for b in all_batches], world)[rank] if world > 1 else list(range(total_utts))
+    local_batches = [all_batches[i] for i in my_idx]
     lib = _native.lib()
 
     def barrier():
@@ -238,24 +248,16 @@ def main():
 
     def step_device(utt_batches):
         """device-resident pass; returns (audio_seconds_local, device_ms, job)"""
-        if world > 1:
-            mine = shard.scatter_ids(utt_batches if rank == 0 else None)
-            job = SynthesisJob(model, mine)
-            ms = job.run(d_out.data_ptr(), out_cap)
-            frames, samples, _ = job.lengths()
-            tot = int(sum(samples))
-            shard.gather_waveforms(d_out[:tot], samples, to_host=False)
-        else:
-            job = SynthesisJob(model, utt_batches)
-            ms = job.run()
-            frames, samples, _ = job.lengths()
+        job = SynthesisJob(model, utt_batches)
+        ms = job.run()
+        frames, samples, _ = job.lengths()
         return sum(samples) / SR, ms, job
 
     # warm-up (the clock sampler starts here so that nvidia-smi is already streaming when the timed region begins)
     sampler = ClockSampler(local_rank)
     sampler.start()
     for _ in range(max(args.warmup, 3)):
-        _, _, j = step_device(all_batches)
+        _, _, j = step_device(local_batches)
         j.close()
 
     prof_acc = {}
@@ -265,7 +267,7 @@ def main():
     t0 = time.perf_counter()
     audio_local, dev_ms = 0.0, 0.0
     for s in range(args.steps):
-        a_, ms, j = step_device(all_batches)
+        a_, ms, j = step_device(local_batches)
         audio_local += a_; dev_ms += ms
         for r in j.profile():
             acc = prof_acc.setdefault(r["name"], {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
@@ -287,32 +289,37 @@ def main():
     value = audio_total / wall_max
 
     # ---------------- e2e: public call, host ids in -> host waveforms out ----------------
+    # Every rank serves its own batch through the public API (`infer_batch_with_values` = speak_batch on ids: ids from
+    # host memory, waveforms into pinned host memory).  The shards are independent -- no data-path collective -- so the
+    # whole-job number is the sum over ranks over the slowest rank's wall time.  The "one frontend on rank 0" variant
+    # (NCCL scatter of the ids, NCCL gather of the waveforms, one device->host copy on rank 0: `shard.py`) is timed
+    # separately below and reported as `e2e.frontend_rank0`; it funnels every GPU's audio through one PCIe link.
+    def step_e2e():
+        auds = model.infer_batch_with_values(local_batches)
+        return sum(len(a) for a in auds) / SR
+
     pinned = {}
 
-    def step_e2e():
-        """host ids (rank 0) -> [NCCL scatter] -> kernels -> [NCCL gather] -> pinned host waveforms (rank 0)"""
-        if world > 1:
-            mine = shard.scatter_ids(all_batches if rank == 0 else None)
-            job = SynthesisJob(model, mine)
-            job.run(d_out.data_ptr(), out_cap)
-            _, samples, _ = job.lengths()
-            tot = int(sum(samples))
-            res = shard.gather_waveforms(d_out[:tot], samples, to_host=False)
-            job.close()
-            if rank != 0:
-                return 0.0
-            gl, owner, lens_all = res
-            n_audio = 0
-            for r_, g_ in enumerate(gl):
-                cnt = int(lens_all[owner == r_].sum())
-                if r_ not in pinned or pinned[r_].numel() < g_.numel():
-                    pinned[r_] = torch.empty(g_.numel(), dtype=torch.float32, pin_memory=True)
-                pinned[r_][:cnt].copy_(g_[:cnt], non_blocking=True)
-                n_audio += cnt
-            torch.cuda.synchronize()
-            return n_audio / SR
-        auds = model.infer_batch_with_values(all_batches)
-        return sum(len(a) for a in auds) / SR
+    def step_frontend():
+        mine = shard.scatter_ids(all_batches if rank == 0 else None)
+        job = SynthesisJob(model, mine)
+        job.run(d_out.data_ptr(), out_cap)
+        _, samples, _ = job.lengths()
+        tot = int(sum(samples))
+        res = shard.gather_waveforms(d_out[:tot], samples, to_host=False)
+        job.close()
+        if rank != 0:
+            return 0.0
+        gl, owner, lens_all = res
+        n_audio = 0
+        for r_, g_ in enumerate(gl):
+            cnt = int(lens_all[owner == r_].sum())
+            if r_ not in pinned or pinned[r_].numel() < g_.numel():
+                pinned[r_] = torch.empty(g_.numel(), dtype=torch.float32, pin_memory=True)
+            pinned[r_][:cnt].copy_(g_[:cnt], non_blocking=True)
+            n_audio += cnt
+        torch.cuda.synchronize()
+        return n_audio / SR
 
     step_e2e()
     barrier()
@@ -326,9 +333,23 @@ def main():
     te = torch.tensor([e2e_wall, e2e_audio], dtype=torch.float64, device="cuda")
     if world > 1:
         tm = te.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        e2e_wall, e2e_audio = float(tm[0]), float(tm[1])
+        tsm = te.clone(); dist.all_reduce(tsm, op=dist.ReduceOp.SUM)
+        e2e_wall, e2e_audio = float(tm[0]), float(tsm[1])
     e2e_value = e2e_audio / e2e_wall
     d2h_bytes = int(4 * e2e_audio * SR / e2e_steps)
+    frontend_value = None
+    if world > 1:
+        step_frontend()
+        barrier()
+        t0 = time.perf_counter()
+        fa = 0.0
+        for _ in range(2):
+            fa += step_frontend()
+        barrier()
+        fw = time.perf_counter() - t0
+        tf_ = torch.tensor([fw, fa], dtype=torch.float64, device="cuda")
+        tm = tf_.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        frontend_value = float(tm[1]) / float(tm[0])
 
     if rank == 0:
         peaks = read_peaks()
@@ -370,11 +391,16 @@ def main():
             "backend": "tcgen05-bf16x2 (flow+decoder), fp32 CUDA cores (encoder, duration predictor)" if args.backend == 1 else "fp32-simt",
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(8 * ids_per_step),
-                    "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps},
+                    "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
+                    "path": "per-rank public call (host ids -> pinned host waveforms), summed over ranks",
+                    "frontend_rank0": frontend_value},
             "roofline": roofline, "regions": regions, "cpu_baseline": cpu_base,
         }
+        sys.stdout.flush()
+        os.dup2(_stdout_fd, 1)
         print(json.dumps(line), flush=True)
         sys.stdout.flush()
+        os.dup2(2, 1)
     model.close()
     if world > 1:
         dist.barrier()
