@@ -13,24 +13,32 @@
 // (tools/micro/mma_bench.cu: 81.4 / 80.1 / 79.6 cycles at N = 32 / 64 / 128), and the hot layers here
 // have N = C_out = 32..128.
 //
-// Data path (no tensor maps needed):
-//   * activations: producer warps cp.async (LDGSTS) the raw (128 + span)-row WINDOW of a K-block from HBM
-//     straight into the smem ring, several stages ahead, then apply the leaky-ReLU prologue, split hi/lo
-//     and rewrite each 128-byte row IN PLACE as  [hi: 32 ch bf16 | lo: 32 ch bf16]  in the canonical
-//     K-major SWIZZLE_128B layout (row r at r*128 B, 16-B chunk c at (c ^ (r & 7))).  A tap is
-//     only a descriptor whose start address is shifted by off_t rows (the swizzle is a function of the
-//     absolute smem address), so a k-tap conv stages its input once and issues k x 6 MMAs on it;
-//   * weights: pre-split, pre-swizzled [hi|lo] tile images written at voice-load time; one
-//     cp.async.bulk (UBLKCP) per (K-block, tap) stage, resident in smem for the whole CTA when they fit;
+// Data path:
+//   * activations: one TMA tensor load per stage (cp.async.bulk.tensor.2d: box = 32 channels x window rows,
+//     unswizzled, zero-filled outside the array; fallbacks: one linear bulk copy when rows are contiguous, or
+//     cp.async / LDGSTS) brings the raw fp32 (128 + span)-row WINDOW of a K-block into the smem ring, several
+//     stages ahead; the producer warps then apply the leaky-ReLU prologue, split hi/lo and rewrite each
+//     128-byte row IN PLACE as  [hi: 32 ch bf16 | lo: 32 ch bf16]  in the canonical K-major SWIZZLE_128B
+//     layout (row r at r*128 B, 16-B chunk c at (c ^ (r & 7))).  A tap is only a descriptor whose start
+//     address is shifted by off_t rows (the swizzle is a function of the absolute smem address), so a k-tap
+//     conv stages its input once and issues k x 6 (cat mode: k x 4) MMAs on it;
+//   * weights: pre-split, pre-swizzled tile images written at voice-load time; one cp.async.bulk (UBLKCP)
+//     per (K-block, tap) stage, resident in smem for the whole CTA when they fit;
 //   * MMA: tcgen05.mma.kind::f16 (UTCHMMA), issued from warp-uniform code under elect.sync;
 //     tcgen05.commit releases ring slots / publishes the accumulator;
-//   * epilogue: tcgen05.ld 32x32b.x32 (LDTM) -> bias / gate / residual / scale / accumulate -> HBM, with
-//     the residual / read-modify-write operands prefetched before the accumulator is awaited.
-// Persistent CTAs (one per SM) walk tiles blockIdx.x, +gridDim.x, ...; three mbarrier pipelines
-// (activation ring, weight ring, 4-stage TMEM accumulator ring) run across tile boundaries.
-// Warps: w0/w1 MMA issuers on alternating tiles (w0 also allocates TMEM), w2 weight producer, w4-7 / w8-11
-// two activation-producer groups, w12-15 / w16-19 two epilogue groups (one per half-pipeline).  Every mbarrier wait carries a watchdog that traps instead of
-// hanging the GPU.
+//   * epilogue, MODE 0 (general): tcgen05.ld 32x32b.x32 (LDTM) -> bias / gate / residual / scale /
+//     accumulate -> HBM with 256-bit row-per-thread accesses, the residual / read-modify-write operands
+//     prefetched before the accumulator is awaited;
+//   * epilogue, MODE 2 (32-channel outputs): residual and read-modify-write tiles arrive by TMA tensor
+//     loads into SWIZZLE_128B staging tiles, the result is written over the residual tile in place and
+//     leaves with one TMA tensor store per tile, all issued by an agent lane of the idle weight warp -- the
+//     SM's load/store path sees no global traffic at all (ncu: that path, not HBM, bounded these layers);
+//   * MODE 1 (opt-in experiment): four taps x 32 channels stacked along N, see plan_stk().
+// Persistent CTAs (one per SM) walk tiles blockIdx.x, +gridDim.x, ...; mbarrier pipelines (activation
+// ring, weight ring, 4-stage TMEM accumulator ring, MODE 2 staging) run across tile boundaries.
+// Warps: w0/w1 MMA issuers on alternating tiles (w0 also allocates TMEM), w2/w3 weight producers and
+// MODE 2 TMA agents, w4-7 / w8-11 two activation-producer groups, w12-15 / w16-19 two epilogue groups (one
+// per half-pipeline).  Every mbarrier wait carries a watchdog that traps instead of hanging the GPU.
 #include "tc_common.cuh"
 #include <cuda.h>
 #include <stdlib.h>
