@@ -54,6 +54,20 @@ struct ConvArgs {
     float* y1; int ldy1; int acc1;                                // columns [split, cout)
 };
 
+// Function attributes (opt-in shared-memory size) are per DEVICE: true the first time the calling site runs on the
+// current device, so that a process driving several GPUs through the C ABI configures each of them.
+struct PerDeviceOnce {
+    unsigned long long mask = 0;
+    bool first() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const unsigned long long bit = 1ull << (dev & 63);
+        if (__atomic_load_n(&mask, __ATOMIC_ACQUIRE) & bit) return false;
+        __atomic_fetch_or(&mask, bit, __ATOMIC_ACQ_REL);
+        return true;
+    }
+};
+
 void launch_conv_simt(const ConvArgs& a, cudaStream_t st);
 int conv_simt_bn_for(int cout);
 bool conv_tc_supported(const ConvArgs& a);

@@ -857,12 +857,11 @@ static int tc_num_sms() {
 
 void launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     if (conv_ts_supported(a)) { launch_conv_ts(a, st); return; }      // experimental transposed kernel (opt-in)
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce once;
+    if (once.first()) {
         cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_done = true;
     }
     TcLaunch L; size_t smem;
     ConvArgs v;

@@ -436,11 +436,8 @@ bool conv_ts_supported(const ConvArgs& a) {
 void launch_conv_ts(const ConvArgs& a, cudaStream_t st) {
     TsLaunch L; size_t smem;
     if (!plan_ts(a, L, smem)) { launch_conv_simt(a, st); return; }
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(conv_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_done = true;
-    }
+    static PerDeviceOnce once;
+    if (once.first()) cudaFuncSetAttribute(conv_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
     const int grid = L.ntiles < sms ? L.ntiles : sms;
