@@ -204,3 +204,21 @@ def test_sharded_synthesize_gloo_world2():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def test_c5_length_buckets_and_completion_stats():
+    """SURVEY §8d C5 scheduling helpers (tools/bench_c5.py): longest-first buckets, latency percentiles."""
+    from sonata_b200 import workload
+    n = workload.mixed_lengths(1024)
+    assert n.shape == (1024,) and n.min() >= 64 and n.max() <= 512
+    assert np.array_equal(n, workload.mixed_lengths(1024))                 # seeded
+    b = workload.length_buckets(n, 32)
+    assert len(b) == 32 and all(len(x) == 32 for x in b)
+    flat = [i for x in b for i in x]
+    assert sorted(flat) == list(range(1024))
+    mx = [max(n[i] for i in x) for x in b]; mn = [min(n[i] for i in x) for x in b]
+    assert all(mn[k] >= mx[k + 1] for k in range(len(b) - 1))              # longest first, non-overlapping ranges
+    assert workload.length_buckets([5, 9, 7], 2) == [[1, 2], [0]]
+    p50, p99, agg = workload.completion_stats([[0, 1], [2]], [1.0, 3.0], [4.0, 2.0])
+    assert p50 == 1.0 and abs(p99 - 2.96) < 1e-9 and agg == 2.0
+    assert workload.completion_stats([], [], []) == (0.0, 0.0, 0.0)
