@@ -1,5 +1,5 @@
 """Per-stage parity report: CUDA path (debug job) vs the torch oracle on the same ids / noise.
-Usage: python tools/stage_report.py [quality] [n_phonemes] [noise: 0|1] [backend]"""
+Test infrastructure (imports the oracle, so it lives under tests/).  Usage: python tests/stage_report.py [quality] [n_phonemes] [noise: 0|1] [backend]"""
 import json
 import os
 import sys

@@ -10,7 +10,8 @@ import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))      # conv_unit.py (kernel unit cases, torch reference only)
+sys.path.insert(0, os.path.join(ROOT, "tests"))      # stage_report.py (uses the oracle: test infrastructure)
 
 import sonata_b200
 from oracle import vits_oracle as vo
