@@ -111,6 +111,94 @@ def gather_waveforms(local_wave: torch.Tensor, local_lens: Sequence[int], group=
     return None
 
 
+class HostGather:
+    """Gather into ONE host buffer without funnelling every GPU's audio through rank 0's PCIe link.
+
+    A POSIX shared-memory segment (grown on demand, reused across calls) is mapped by every rank; each rank copies its
+    own waveforms device->host into its slice -- N links in parallel -- and rank 0 reads all of them from the same
+    pages.  The collectives carry only the length table and the segment's name.  With `pin=True` on a CUDA build the
+    mapping is page-locked (`cudaHostRegister`) so the copies are DMA transfers.  (NCCL gather + one copy reached
+    80k audio-s/s at N = 8 where per-rank host buffers reach 174k: profiles/notes_r01.md.)
+    """
+
+    def __init__(self, group=None, pin: bool = True):
+        self.group, self.pin = group, pin
+        self.shm = None
+        self.cap = 0
+        self._registered = None
+
+    def _ensure(self, nbytes: int):
+        from multiprocessing import shared_memory
+        rank = dist.get_rank(self.group)
+        need = torch.tensor([int(nbytes > self.cap)], dtype=torch.int64, device=_dev(self.group))
+        dist.all_reduce(need, op=dist.ReduceOp.MAX, group=self.group)
+        if int(need.item()) == 0:
+            return
+        self.close(unlink=rank == 0)
+        cap = max(int(nbytes * 1.25), 1 << 20)
+        name = [None]
+        if rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=cap)
+            name[0] = self.shm.name
+        dist.broadcast_object_list(name, src=0, group=self.group)
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name[0])
+        self.cap = cap
+        if self.pin and torch.cuda.is_available() and dist.get_backend(self.group) == "nccl":
+            buf = np.frombuffer(self.shm.buf, dtype=np.uint8)
+            if int(torch.cuda.cudart().cudaHostRegister(buf.ctypes.data, cap, 0)) == 0:
+                self._registered = buf.ctypes.data     # on failure the copies still work, through pageable memory
+        dist.barrier(group=self.group)
+
+    def gather(self, local_wave: torch.Tensor, local_lens: Sequence[int]):
+        """Same contract as `gather_waveforms(..., to_host=True)`: rank 0 returns the waveforms in GLOBAL utterance
+        order (views into the shared segment, valid until the next call), other ranks return None."""
+        rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        dev = _dev(self.group)
+        info = scatter_ids.last
+        n, owner, mine = info["n"], info["owner"], info["mine"]
+        lens = torch.zeros(n, dtype=torch.int64, device=dev)
+        if len(mine):
+            lens[torch.from_numpy(mine).to(dev)] = torch.tensor(list(local_lens), dtype=torch.int64, device=dev)
+        dist.all_reduce(lens, group=self.group)
+        lens_all = lens.cpu().numpy()
+        offs = np.zeros(n + 1, dtype=np.int64)
+        order = [i for r in range(world) for i in np.nonzero(owner == r)[0]]      # rank-major layout of the segment
+        pos = 0
+        for i in order:
+            offs[i] = pos
+            pos += int(lens_all[i])
+        self._ensure(pos * 4)
+        seg = np.frombuffer(self.shm.buf, dtype=np.float32, count=self.cap // 4)
+        my_tot = int(lens_all[mine].sum()) if len(mine) else 0
+        if my_tot:
+            start = int(offs[mine[0]])                                            # a rank's utterances are contiguous
+            torch.from_numpy(seg[start:start + my_tot]).copy_(local_wave[:my_tot])
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        if rank != 0:
+            return None
+        return [seg[int(offs[i]):int(offs[i]) + int(lens_all[i])] for i in range(n)]
+
+    def close(self, unlink: bool = False):
+        if self.shm is None:
+            return
+        if self._registered is not None:
+            torch.cuda.cudart().cudaHostUnregister(self._registered)
+            self._registered = None
+        try:
+            self.shm.close()
+        except BufferError:
+            pass                                   # views handed out by gather() are still alive
+        if unlink:
+            try:
+                self.shm.unlink()
+            except FileNotFoundError:
+                pass
+        self.shm, self.cap = None, 0
+
+
 def sharded_synthesize(batches: Optional[Sequence[np.ndarray]], synth: Callable[[List[np.ndarray]], List[np.ndarray]],
                        group=None) -> Optional[List[np.ndarray]]:
     """scatter -> local synthesis (`synth`: list of id arrays -> list of float32 waveforms) -> gather."""
