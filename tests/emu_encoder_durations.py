@@ -62,7 +62,7 @@ def main():
     schemes = [("fp32 (oracle as is)", None), ("bf16x2, truncating acc", ("bf16", "rz", 0)),
                ("3xTF32, truncating acc", ("tf32", "rz", 0)), ("3xTF32, flush / 8 K-steps", ("tf32", "rz", 8)),
                ("3xTF32, flush / 4 K-steps", ("tf32", "rz", 4))]
-    res = {name: [0.0, 0, 0] for name, _ in schemes}                              # max err, flips vs fp64, flips vs fp32
+    res = {name: [0.0, 0, 0, 0.0, []] for name, _ in schemes}     # max err, flips vs fp64, flips vs fp32, sum |dw|, errs
     total = 0
     with torch.inference_mode():
         for u in range(n_utts):
@@ -85,12 +85,17 @@ def main():
                 r = res[name]
                 r[0] = max(r[0], float(np.abs(lw - ref).max()))
                 r[1] += int((d != d_ref).sum()); r[2] += int((d != d_base).sum())
+                # a frame count flips when w = exp(logw) and its fp64 value straddle an integer: for a uniformly
+                # distributed fractional part that happens with probability |dw|
+                r[3] += float(np.abs(np.exp(lw.astype(np.float64)) - np.exp(ref)).sum())
+                r[4].append(np.abs(lw - ref))
             print(f"utterance {u + 1}/{n_utts} done", flush=True)
     print(f"\n{total} ids ({n_utts} x {nph} phonemes), medium voice, noise_w = 0")
-    print(f"{'scheme':32s} {'max|logw-fp64|':>15s} {'flips vs fp64':>14s} {'flips vs fp32':>14s}")
+    print(f"{'scheme':32s} {'max|logw-fp64|':>15s} {'median':>10s} {'flips vs fp64':>14s} {'flips vs fp32':>14s} {'E[flips] / 16448 ids':>22s}")
     for name, _ in schemes:
         r = res[name]
-        print(f"{name:32s} {r[0]:15.2e} {r[1]:14d} {r[2]:14d}")
+        med = float(np.median(np.concatenate(r[4])))
+        print(f"{name:32s} {r[0]:15.2e} {med:10.2e} {r[1]:14d} {r[2]:14d} {r[3] / total * 16448:22.3f}")
 
 
 if __name__ == "__main__":
