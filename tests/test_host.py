@@ -2,6 +2,7 @@
 the weight container and the N>1 sharding plumbing (gloo, world_size 2)."""
 import ctypes
 import os
+import sys
 import re
 
 import numpy as np
@@ -265,3 +266,25 @@ def test_c5_length_buckets_and_completion_stats():
     p50, p99, agg = workload.completion_stats([[0, 1], [2]], [1.0, 3.0], [4.0, 2.0])
     assert p50 == 1.0 and abs(p99 - 2.96) < 1e-9 and agg == 2.0
     assert workload.completion_stats([], [], []) == (0.0, 0.0, 0.0)
+
+
+def test_tensor_core_emulation_primitives():
+    """tools/emu_tc_accuracy.py (round-2 planning): operand rounding matches torch's bf16 cast, the truncating fp32
+    conversion never rounds away from zero, and flushing the accumulator reduces the error of a long contraction."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import emu_tc_accuracy as emu
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal(4096) * np.exp(rng.uniform(-20, 20, 4096))).astype(np.float32)
+    assert np.array_equal(emu.round_to_bits(x, 8), torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy())
+    hi = emu.round_to_bits(x, 11)
+    assert np.all(np.abs(hi - x) <= np.abs(x) * 2.0 ** -11) and np.all((hi.view(np.uint32) & 0x1FFF) == 0)
+    v = rng.standard_normal(2048) * 1e3
+    rz = emu.to_f32(v, "rz").astype(np.float64)
+    assert np.all(np.abs(rz) <= np.abs(v)) and np.all(np.abs(rz - v) <= np.abs(v) * 2.0 ** -23)
+    a = rng.standard_normal((16, 1024)).astype(np.float32)
+    b = (rng.standard_normal((1024, 8)) / 32).astype(np.float32)
+    ref = a.astype(np.float64) @ b.astype(np.float64)
+    plain = np.abs(emu.emulate(a, b, "tf32", "rz", 0) - ref).max()
+    chunked = np.abs(emu.emulate(a, b, "tf32", "rz", 8) - ref).max()
+    assert chunked < plain and chunked < 5e-6
