@@ -356,7 +356,11 @@ int32_t sb200_debug_conv(int32_t device, int32_t backend, const float* x, int32_
         long long* dtrace = nullptr;
         const bool want_trace = backend == 1 && getenv("SB200_TC_TRACE") != nullptr;
         if (want_trace) { SB_CUDA(cudaMalloc(&dtrace, 48 * 8 * 8)); SB_CUDA(cudaMemset(dtrace, 0, 48 * 8 * 8)); }
-        if (backend == 1) {
+        p.wtf = cw.wtf;
+        if (backend == 2) {
+            if (!conv_tf_supported(p)) throw Error(19, "conv shape not supported by the tf32 chunk-flush backend");
+            launch_conv_tf(p, 0);
+        } else if (backend == 1) {
             if (!conv_tc_supported(p)) throw Error(19, "conv shape not supported by the tcgen05 backend");
             if (want_trace) launch_conv_tc(p, 0); // warm-up before the traced run (timing only: RMW cases run twice)
             p.trace = dtrace;

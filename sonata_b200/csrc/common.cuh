@@ -11,6 +11,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
 
 #define SB_MAX_TAPS 16
 
@@ -43,6 +44,7 @@ struct ConvArgs {
     const float* wtc; int tc_nt;                                  // tcgen05 weight images (conv_tc.cu) or null
     const float* wts;                                             // tap-stacked weight images (conv_ts.cu) or null
     const float* wcat;                                            // hi/lo-stacked tap-pair images (conv_tc.cu cat mode) or null
+    const float* wtf;                                             // tf32 hi/lo images (conv_tf.cu) or null
     int ntaps; int tap_off[SB_MAX_TAPS]; int min_off; int span;   // span = max_off - min_off
     int rows_q; int orow_mul; int orow_add;
     int phase_cols;                                               // >0: fused polyphase ConvTranspose (tcgen05 path only)
@@ -54,17 +56,22 @@ struct ConvArgs {
     float* y1; int ldy1; int acc1;                                // columns [split, cout)
 };
 
-// Function attributes (opt-in shared-memory size) are per DEVICE: true the first time the calling site runs on the
-// current device, so that a process driving several GPUs through the C ABI configures each of them.
+// Function attributes (opt-in shared-memory size) are per DEVICE: `run` executes `f` the first time the calling site
+// runs on the current device (a process driving several GPUs through the C ABI configures each of them).  The device
+// bit is published only AFTER `f` returned, under a mutex, so a second host thread on the same device can never
+// launch with more than 48 KB of dynamic shared memory before the opt-in has been applied.
 struct PerDeviceOnce {
-    unsigned long long mask = 0;
-    bool first() {
+    std::mutex mu;
+    unsigned long long done = 0;
+    template <typename F> void run(F&& f) {
         int dev = 0;
         cudaGetDevice(&dev);
         const unsigned long long bit = 1ull << (dev & 63);
-        if (__atomic_load_n(&mask, __ATOMIC_ACQUIRE) & bit) return false;
-        __atomic_fetch_or(&mask, bit, __ATOMIC_ACQ_REL);
-        return true;
+        if (__atomic_load_n(&done, __ATOMIC_ACQUIRE) & bit) return;
+        std::lock_guard<std::mutex> g(mu);
+        if (done & bit) return;
+        f();
+        __atomic_fetch_or(&done, bit, __ATOMIC_RELEASE);
     }
 };
 
@@ -76,6 +83,10 @@ size_t conv_tc_weight_floats(int cin, int cout, int ntaps, int nt);
 void conv_tc_build_weights(const float* wt, int ldw, int cin, int cout, int ntaps, int nt, float* out);
 size_t conv_tc_cat_weight_floats(int cin, int cout, int ntaps, int nt);
 void conv_tc_build_weights_cat(const float* wt, int ldw, int cin, int cout, int ntaps, int nt, float* out);
+bool conv_tf_supported(const ConvArgs& a);
+void launch_conv_tf(const ConvArgs& a, cudaStream_t st);
+size_t conv_tf_weight_floats(int cin, int cout, int ntaps);
+void conv_tf_build_weights(const float* wt, int ldw, int cin, int cout, int ntaps, float* out);
 bool conv_ts_supported(const ConvArgs& a);
 void launch_conv_ts(const ConvArgs& a, cudaStream_t st);
 size_t conv_ts_weight_floats(int ntaps);

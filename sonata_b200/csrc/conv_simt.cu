@@ -210,7 +210,7 @@ void launch_cfg(const ConvArgs& a, cudaStream_t st) {
     constexpr int BN = TX * VW * NV;
     auto kern = conv_simt_kernel<BM, TX, VW, NV>;
     static PerDeviceOnce once;
-    if (once.first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    once.run([&] { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); });
     const size_t smem = ((size_t)2 * (BM + a.span) * AS_STRIDE + 2 * BK * BN) * sizeof(float);
     dim3 grid((a.rows_q + BM - 1) / BM, a.ldw / BN);
     kern<<<grid, 256, smem, st>>>(a);

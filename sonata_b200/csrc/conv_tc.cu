@@ -43,6 +43,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unordered_map>
 
 namespace sb200 {
 
@@ -690,46 +691,15 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
     }
 }
 
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
-typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-TensorMapEncodeFn tensor_map_encoder() {
-    static TensorMapEncodeFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<TensorMapEncodeFn>(p);
-        cudaGetLastError();
-    }
-    return fn;
-}
-
 // [rows][32] fp32 view of an output buffer: 128 x 32 boxes, SWIZZLE_128B in shared memory
 bool make_out_map(CUtensorMap* tm, float* base, int rows, int ld) {
-    const cuuint64_t dims[2] = {32, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    const cuuint32_t box[2] = {32, 128};
-    const cuuint32_t estr[2] = {1, 1};
-    return tensor_map_encoder()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return tensor_map_2d(tm, base, 32, (unsigned long long)rows, (unsigned long long)ld, 32, 128, true);
 }
 
 // [rows][cin] fp32 view of a conv input: boxes of 32 channels x win rows, linear (unswizzled) in shared memory --
 // exactly the raw window image the producers convert in place
 bool make_in_map(CUtensorMap* tm, const float* base, int rows, int cin, int ld, int win) {
-    const cuuint64_t dims[2] = {(cuuint64_t)cin, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    const cuuint32_t box[2] = {32, (cuuint32_t)win};
-    const cuuint32_t estr[2] = {1, 1};
-    return tensor_map_encoder()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return tensor_map_2d(tm, base, (unsigned long long)cin, (unsigned long long)rows, (unsigned long long)ld, 32, (unsigned)win, false);
 }
 
 // 256-bit epilogue accesses need 32-byte aligned rows and column blocks for every operand that is used
@@ -843,6 +813,39 @@ float bf16_to_float_host(uint16_t h) {
 
 }  // namespace
 
+bool tensor_map_2d(CUtensorMap* tm, const void* base, unsigned long long cols, unsigned long long rows, unsigned long long ld,
+                   unsigned box_cols, unsigned box_rows, bool swizzle128) {
+    TensorMapEncodeFn enc = tensor_map_encoder();
+    if (!enc) return false;
+    struct Key {
+        const void* base; unsigned long long cols, rows, ld; unsigned bc, br; bool sw;
+        bool operator==(const Key& o) const { return base == o.base && cols == o.cols && rows == o.rows && ld == o.ld && bc == o.bc && br == o.br && sw == o.sw; }
+    };
+    struct Hash {
+        size_t operator()(const Key& k) const {
+            size_t h = reinterpret_cast<size_t>(k.base);
+            for (unsigned long long v : {k.cols, k.rows, k.ld, (unsigned long long)k.bc, (unsigned long long)k.br, (unsigned long long)k.sw})
+                h = (h ^ (size_t)v) * 0x9E3779B97F4A7C15ull;
+            return h;
+        }
+    };
+    thread_local std::unordered_map<Key, CUtensorMap, Hash> cache;
+    const Key key{base, cols, rows, ld, box_cols, box_rows, swizzle128};
+    auto it = cache.find(key);
+    if (it != cache.end()) { *tm = it->second; return true; }
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    if (enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    if (cache.size() > 4096) cache.clear();
+    cache.emplace(key, *tm);
+    return true;
+}
+
 bool conv_tc_supported(const ConvArgs& a) {
     TcLaunch L; size_t smem;
     if (a.cin % 32 || a.cout % 32 || a.ntaps > SB_MAX_TAPS) return false;
@@ -858,11 +861,11 @@ static int tc_num_sms() {
 void launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     if (conv_ts_supported(a)) { launch_conv_ts(a, st); return; }      // experimental transposed kernel (opt-in)
     static PerDeviceOnce once;
-    if (once.first()) {
+    once.run([] {
         cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    }
+    });
     TcLaunch L; size_t smem;
     ConvArgs v;
     CUtensorMap tm, tmr, tmx;

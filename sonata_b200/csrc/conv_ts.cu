@@ -437,7 +437,7 @@ void launch_conv_ts(const ConvArgs& a, cudaStream_t st) {
     TsLaunch L; size_t smem;
     if (!plan_ts(a, L, smem)) { launch_conv_simt(a, st); return; }
     static PerDeviceOnce once;
-    if (once.first()) cudaFuncSetAttribute(conv_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    once.run([] { cudaFuncSetAttribute(conv_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
     const int grid = L.ntiles < sms ? L.ntiles : sms;

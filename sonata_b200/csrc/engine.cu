@@ -148,18 +148,22 @@ struct Runner {
         float* y1 = nullptr; int ldy1 = 0; int acc1 = 0;
         int orow_mul = 1, orow_add = 0;
         bool tc_ok = false;
+        bool tf_ok = false;    // duration-critical layer: tcgen05 3xTF32 with chunk-flushed accumulation (conv_tf.cu)
     };
     void conv(const ConvW& w, const float* x, int ldx, const Level& lin, const Opt& o) {
         ConvArgs p{};
         p.x = x; p.ldx = ldx; p.rows_in = lin.map.rows; p.cin = w.cin; p.in_slope = o.in_slope;
-        p.w = w.w; p.bias = w.bias; p.ldw = w.ldw; p.cout = w.cout; p.wtc = w.wtc; p.tc_nt = w.tc_nt; p.wts = w.wts; p.wcat = w.wcat;
+        p.w = w.w; p.bias = w.bias; p.ldw = w.ldw; p.cout = w.cout; p.wtc = w.wtc; p.tc_nt = w.tc_nt; p.wts = w.wts; p.wcat = w.wcat; p.wtf = w.wtf;
         p.ntaps = w.ntaps; memcpy(p.tap_off, w.tap_off, sizeof(p.tap_off)); p.min_off = w.min_off; p.span = w.span;
         p.rows_q = lin.map.rows; p.orow_mul = o.orow_mul; p.orow_add = o.orow_add;
         p.map = lin.map;
         p.act = o.act; p.scale = o.scale; p.res = o.res; p.ldres = o.ldres;
         p.y0 = o.y0; p.ldy0 = o.ldy0; p.acc0 = o.acc0; p.split = o.split < 0 ? w.cout : o.split;
         p.y1 = o.y1; p.ldy1 = o.ldy1; p.acc1 = o.acc1;
-        if (v.backend == 1 && o.tc_ok && conv_tc_supported(p)) launch_conv_tc(p, st);
+        // backend 1 (default): tcgen05 everywhere; 2: tcgen05 flow / decoder, fp32 CUDA cores for the text encoder and
+        // the duration predictor (the round-1 configuration, kept for A/B runs); 0: fp32 CUDA cores everywhere
+        if (v.backend == 1 && o.tf_ok && conv_tf_supported(p)) launch_conv_tf(p, st);
+        else if (v.backend >= 1 && o.tc_ok && conv_tc_supported(p)) launch_conv_tc(p, st);
         else launch_conv_simt(p, st);
         const double vr = (double)lin.valid_rows;
         const int cout_w = (o.act == ACT_GATE) ? w.cout / 2 : w.cout;
@@ -174,7 +178,7 @@ struct Runner {
         for (int i = 0; i < 3; i++) {
             launch_dw_ln_gelu(x, d.wdw[i], d.bdw[i], a.dp_kernel, dil, d.g1[i], d.b1[i], t1, C, L.map, st);
             count(2.0 * L.valid_rows * C * a.dp_kernel, 8.0 * L.valid_rows * C);
-            Opt o; o.y0 = t2; o.ldy0 = C;
+            Opt o; o.y0 = t2; o.ldy0 = C; o.tf_ok = true;
             conv(d.c1x1[i], t1, C, L, o);
             launch_ln(t2, nullptr, x, d.g2[i], d.b2[i], x, C, 1, L.map, st);
             count(0, 12.0 * L.valid_rows * C);
@@ -221,7 +225,7 @@ void run_decoder(Runner& R, const Level& LY, const float* s, float* d_wav, const
         }
         R.begin("dec.up" + std::to_string(i));
         bool fused_done = false;
-        if (v.backend == 1 && st.fused.wtc) {
+        if (v.backend >= 1 && st.fused.wtc) {
             // tcgen05 path: all u phases in one launch (input read once, N = u*cout columns)
             ConvArgs pa{};
             pa.x = cur; pa.ldx = st.cin; pa.rows_in = Lin.map.rows; pa.cin = st.cin; pa.in_slope = 0.1f;
@@ -411,32 +415,32 @@ void Job::run(float* d_out, size_t d_out_cap) {
     R.count(0, 4.0 * LX.valid_rows * H);
     for (int l = 0; l < a.layers; l++) {
         const EncLayer& e = V.enc[l];
-        { Runner::Opt o; o.y0 = qkv; o.ldy0 = 3 * H; R.conv(e.qkv, xa, H, LX, o); }
+        { Runner::Opt o; o.y0 = qkv; o.ldy0 = 3 * H; o.tf_ok = true; R.conv(e.qkv, xa, H, LX, o); }
         launch_attention(qkv, 3 * H, e.relk, e.relv, a.window, att, H, H, a.heads, d_xsegs, (int)B, max_tx, st);
         { double f = 0; for (auto& s : xsegs) f += 4.0 * (double)s.len * s.len * H; R.count(f, 16.0 * LX.valid_rows * H); }
-        { Runner::Opt o; o.y0 = xb; o.ldy0 = H; R.conv(e.o, att, H, LX, o); }
+        { Runner::Opt o; o.y0 = xb; o.ldy0 = H; o.tf_ok = true; R.conv(e.o, att, H, LX, o); }
         launch_ln(xa, xb, nullptr, e.g1, e.b1, xa, H, 0, LX.map, st);
         R.count(0, 12.0 * LX.valid_rows * H);
-        { Runner::Opt o; o.act = ACT_RELU; o.y0 = ffn; o.ldy0 = F; R.conv(e.ffn1, xa, H, LX, o); }
-        { Runner::Opt o; o.y0 = xb; o.ldy0 = H; R.conv(e.ffn2, ffn, F, LX, o); }
+        { Runner::Opt o; o.act = ACT_RELU; o.y0 = ffn; o.ldy0 = F; o.tf_ok = true; R.conv(e.ffn1, xa, H, LX, o); }
+        { Runner::Opt o; o.y0 = xb; o.ldy0 = H; o.tf_ok = true; R.conv(e.ffn2, ffn, F, LX, o); }
         launch_ln(xa, xb, nullptr, e.g2, e.b2, xa, H, 0, LX.map, st);
         R.count(0, 12.0 * LX.valid_rows * H);
     }
-    { Runner::Opt o; o.y0 = stats; o.ldy0 = 2 * I; o.tc_ok = true; R.conv(V.enc_proj, xa, H, LX, o); }
+    { Runner::Opt o; o.y0 = stats; o.ldy0 = 2 * I; o.tf_ok = true; R.conv(V.enc_proj, xa, H, LX, o); }
     R.end();
     if (debug) { dbg["x"] = {xa, H}; dbg_level["x"] = 0; dbg["stats"] = {stats, 2 * I}; dbg_level["stats"] = 0; }
 
     // ---------------- stochastic duration predictor (reverse) ----------------
     R.begin("dp");
-    { Runner::Opt o; o.y0 = d0; o.ldy0 = H; R.conv(V.dp_pre, xa, H, LX, o); }
+    { Runner::Opt o; o.y0 = d0; o.ldy0 = H; o.tf_ok = true; R.conv(V.dp_pre, xa, H, LX, o); }
     R.dds(V.dp_dds, d0, t1, t2, LX);
-    { Runner::Opt o; o.y0 = g; o.ldy0 = H; R.conv(V.dp_proj, d0, H, LX, o); }
+    { Runner::Opt o; o.y0 = g; o.ldy0 = H; o.tf_ok = true; R.conv(V.dp_proj, d0, H, LX, o); }
     launch_scale_copy2(d_epsw, cfg.noise_w, zz, LX.map, st);
     for (const CFlowW& cf : V.dp_flows) {
         launch_flow_pre(zz, cf.ccol, cf.pre_w, cf.pre_b, g, d0, H, LX.map, st);
         R.count(2.0 * LX.valid_rows * H, 8.0 * LX.valid_rows * H);
         R.dds(cf.dds, d0, t1, t2, LX);
-        { Runner::Opt o; o.y0 = h29; o.ldy0 = 32; R.conv(cf.proj, d0, H, LX, o); }
+        { Runner::Opt o; o.y0 = h29; o.ldy0 = 32; o.tf_ok = true; R.conv(cf.proj, d0, H, LX, o); }
         launch_spline(h29, 32, zz, cf.tcol, a.dp_bins, 1.0f / sqrtf((float)H), LX.map, st);
         R.count(0, 4.0 * LX.valid_rows * 34);
     }

@@ -51,6 +51,7 @@ struct ConvW {
     float* wtc = nullptr; int tc_nt = 0;     // tcgen05 hi/lo swizzled weight images
     float* wts = nullptr;                    // tap-stacked images for the 32-channel layers (conv_ts.cu)
     float* wcat = nullptr;                   // hi/lo-stacked tap-pair images (conv_tc.cu cat mode), column tiles <= 64
+    float* wtf = nullptr;                    // tf32 hi/lo images (conv_tf.cu): text-encoder / duration-predictor layers
     int cin = 0, cout = 0, ldw = 0, ntaps = 0;
     int tap_off[SB_MAX_TAPS] = {0};
     int min_off = 0, span = 0;
@@ -98,7 +99,9 @@ struct Voice {
     int c_last = 0;
     size_t weight_bytes = 0;
 
-    int backend = 1;                // 1 (default) tcgen05 bf16x2 for flow + decoder contractions, 0 = fp32 CUDA cores everywhere
+    int backend = 1;                // 1 (default): tcgen05 everywhere (bf16x2 split for flow + decoder, chunk-flushed 3xTF32 for the text
+                                    // encoder + duration predictor); 2: tcgen05 flow + decoder, fp32 CUDA cores for encoder + predictor;
+                                    // 0: fp32 CUDA cores everywhere
     unsigned long long noise_seed = 0x5eed5eedULL;
     std::mutex pool_mu;
     std::vector<Context*> pool;

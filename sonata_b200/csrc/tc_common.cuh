@@ -2,6 +2,7 @@
 // fences / commit / MMA / TMEM loads, shared-space vector accesses, the bf16 hi/lo splitter.
 #pragma once
 #include "common.cuh"
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdio.h>
 
@@ -155,4 +156,30 @@ __device__ __forceinline__ uint32_t split2(float a, float b, uint32_t& lo) {
 #endif
 
 }  // namespace tcx
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline TensorMapEncodeFn tensor_map_encoder() {
+    static TensorMapEncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<TensorMapEncodeFn>(p);
+        cudaGetLastError();
+        tried = true;
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor map [rows][cols] (row stride ld floats), box = box_cols x box_rows, zero fill outside the array.
+// Encoding costs ~1-2 us on the host and the same few (buffer, shape) combinations recur launch after launch (the
+// arena hands out the same addresses for the same batch shape), so the encoded maps are cached per host thread.
+bool tensor_map_2d(CUtensorMap* tm, const void* base, unsigned long long cols, unsigned long long rows, unsigned long long ld,
+                   unsigned box_cols, unsigned box_rows, bool swizzle128);
+
 }  // namespace sb200

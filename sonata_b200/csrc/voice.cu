@@ -61,6 +61,7 @@ const HostTensor& T(const TensorMap& m, const std::string& n) {
 
 struct Uploader {
     Voice* v;
+    bool want_tf = false;      // also build the tf32 hi/lo images of conv_tf.cu (layers that feed the duration predictor)
     float* up(const std::vector<float>& h) {
         float* d = nullptr;
         SB_CUDA(cudaMalloc(&d, h.size() * sizeof(float) + 16));
@@ -81,6 +82,14 @@ int tc_tile_for(int cout) {
 // tcgen05 weight images for a finished ConvW whose [ntaps][cin][ldw] host copy is `wt`
 void add_tc_images(Uploader& U, ConvW& c, const std::vector<float>& wt) {
     if (c.cin % 32 || c.cout % 32) return;
+    if (U.want_tf && c.ldw >= c.cout) {
+        const size_t nf = conv_tf_weight_floats(c.cin, c.cout, c.ntaps);
+        if (nf) {
+            std::vector<float> img(nf);
+            conv_tf_build_weights(wt.data(), c.ldw, c.cin, c.cout, c.ntaps, img.data());
+            c.wtf = U.up(img);
+        }
+    }
     const int nt = tc_tile_for(c.cout);
     if (!nt) return;
     std::vector<float> img(conv_tc_weight_floats(c.cin, c.cout, c.ntaps, nt));
@@ -193,6 +202,7 @@ ConvW debug_make_conv(Voice& v, const float* w, const float* bias, int cout, int
     hb.dims = {cout}; hb.f.assign(cout, 0.f);
     if (bias) hb.f.assign(bias, bias + cout);
     Uploader U{&v};
+    U.want_tf = true;
     return make_conv(U, {&hw}, {&hb}, dil);
 }
 
@@ -322,6 +332,7 @@ Voice* load_voice(const std::string& config_path, int device) {
     if (D != 96 && D != 48) throw Error(17, "unsupported attention head size");
 
     Uploader U{v.get()};
+    U.want_tf = true;          // text encoder + duration predictor: error-compensated tf32 with chunked accumulation
     v->emb = U.up(T(m, "enc_p.emb.weight").f);
     for (int l = 0; l < a.layers; l++) {
         EncLayer e;
@@ -363,6 +374,7 @@ Voice* load_voice(const std::string& config_path, int device) {
         v->ea_m0 = T(m, "dp.flows.0.m").f[0];
         v->ea_logs0 = T(m, "dp.flows.0.logs").f[0];
     }
+    U.want_tf = false;
     {
         const int half = I / 2;
         std::vector<int> rev(half);

@@ -17,7 +17,9 @@ from sonata_b200.job import SynthesisJob  # noqa: E402
 from sonata_b200.piper import PiperSynthesisConfig  # noqa: E402
 
 
-def stage_report(quality="medium", n_list=(16,), noise=False, backend=0, seed=1234, verbose=True):
+def stage_report(quality="medium", n_list=(16,), noise=False, backend=0, seed=1234, verbose=True, utts=None):
+    """utts: utterance seeds (default 0, 1, ...: the index in n_list); tests/screen_margin.py picks seeds whose
+    durations are well clear of the ceil() cliff for the full-size cases."""
     cfg_path = voicegen.write_voice(voicegen.default_voice_dir(), quality, seed)
     W = vo.to_torch(voicegen.make_tensors(quality, seed))
     a = vo.arch_of(W)
@@ -25,7 +27,8 @@ def stage_report(quality="medium", n_list=(16,), noise=False, backend=0, seed=12
     model.set_backend(backend)
     scales = [0.667, 1.0, 0.8] if noise else [0.0, 1.0, 0.0]
     model.set_fallback_synthesis_config(PiperSynthesisConfig(None, scales[0], scales[1], scales[2]))
-    batches = [vo.synthetic_ids(n, utt=i) for i, n in enumerate(n_list)]
+    utts = list(range(len(n_list))) if utts is None else list(utts)
+    batches = [vo.synthetic_ids(n, utt=u) for u, n in zip(utts, n_list)]
     g = torch.Generator().manual_seed(99)
     refs, eps_w, eps_z = [], [], []
     for ids in batches:
@@ -63,7 +66,9 @@ def stage_report(quality="medium", n_list=(16,), noise=False, backend=0, seed=12
         tm = lambda t: t[0].T.numpy()   # [1,C,T] -> [T,C]
         cmp("x", job.debug_fetch("x", b), tm(st["x"]))
         cmp("stats", job.debug_fetch("stats", b), np.concatenate([tm(st["m_p"]), tm(st["logs_p"])], 1))
-        cmp("logw", job.debug_fetch("logw", b), tm(st["logw"]))
+        logw_got = job.debug_fetch("logw", b)
+        cmp("logw", logw_got, tm(st["logw"]))
+        logw_med = float(np.median(np.abs(np.asarray(logw_got, dtype=np.float64) - tm(st["logw"]).astype(np.float64))))
         cum = job.durations(b)
         ref_cum = np.cumsum(st["w_ceil"].view(-1).numpy()).astype(np.int64)
         dur_ok = bool(np.array_equal(cum.astype(np.int64), ref_cum))
@@ -79,8 +84,9 @@ def stage_report(quality="medium", n_list=(16,), noise=False, backend=0, seed=12
         w = st["w"].view(-1)
         fr = w - torch.floor(w)
         margin = float(torch.minimum(fr, 1 - fr).min())
-        u = {"n_ids": len(ids), "y_len_ref": st["y_len"], "y_len_got": frames[b], "durations_exact": dur_ok,
-             "ceil_margin": margin, "stages": [(r[0], r[1], r[2]) for r in rows]}
+        n_flip = int((np.diff(np.concatenate([[0], cum.astype(np.int64)])) != np.diff(np.concatenate([[0], ref_cum]))).sum())
+        u = {"n_ids": len(ids), "utt": utts[b], "y_len_ref": st["y_len"], "y_len_got": frames[b], "durations_exact": dur_ok,
+             "ceil_margin": margin, "flipped_ids": n_flip, "logw_median_err": logw_med, "stages": [(r[0], r[1], r[2]) for r in rows]}
         report["utts"].append(u)
         if verbose:
             print(f"--- {quality} utt {b}: T_x={len(ids)} y_len ref/got={st['y_len']}/{frames[b]} "

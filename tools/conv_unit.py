@@ -87,11 +87,34 @@ CASES = [
     (148 * 128 * 4, 32, 32, 11, 5, 0.1, 0, False, 1.0, True, 148 * 128 * 4 - 1000),
 ]
 
+# backend 2 = conv_tf.cu (tcgen05 3xTF32 with chunk-flushed accumulation; the text-encoder / duration-predictor
+# layers): fp32-class accuracy is the point, so these cases are held to TF_TOL against the fp64 reference (the fp32
+# FMA chain of backend 0 measures 2e-6 .. 1e-5 on the same cases).  Shapes: every (cin, cout, k) of the encoder and
+# the duration predictor, all three column tiles (96 / 64 / 32), ragged row counts (odd number of 128-row tiles in
+# the last pair), residual / scale / accumulate / masked rows, a leaky-ReLU prologue, and multi-tile persistent runs.
+TF_TOL = 1.5e-5
+TF_CASES = [
+    (256, 192, 576, 1, 1, 1.0, 0, False, 1.0, False, None),
+    (256, 192, 192, 1, 1, 1.0, 0, False, 1.0, False, None),
+    (256, 192, 768, 3, 1, 1.0, 1, False, 1.0, False, None),
+    (256, 768, 192, 3, 1, 1.0, 0, False, 1.0, False, None),
+    (256, 192, 384, 1, 1, 1.0, 0, False, 1.0, False, None),
+    (256, 192, 32, 1, 1, 1.0, 0, False, 1.0, False, None),
+    (300, 192, 192, 1, 1, 1.0, 0, True, 0.5, True, 290),
+    (640, 64, 64, 3, 1, 1.0, 0, True, 1.0, False, 600),
+    (384, 96, 128, 5, 2, 0.1, 0, False, 1.0, False, 380),
+    (128, 32, 32, 1, 1, 1.0, 0, False, 1.0, False, 100),
+    (148 * 256 * 2 + 300, 192, 192, 3, 1, 1.0, 0, False, 1.0, False, 148 * 256 * 2 + 17),
+    (18432, 192, 576, 1, 1, 1.0, 0, False, 1.0, False, 18000),
+    (18432, 768, 192, 3, 1, 1.0, 0, True, 1.0, False, None),
+    (18432 + 128, 192, 768, 3, 1, 1.0, 1, False, 1.0, False, None),
+]
+
 if __name__ == "__main__":
     backend = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-    cases = CASES
+    cases = TF_CASES if backend == 2 else CASES
     if len(sys.argv) > 2:      # "quick" = first three cases, or a comma-separated list of case indices
-        cases = CASES[:3] if sys.argv[2] == "quick" else [CASES[int(i)] for i in sys.argv[2].split(",")]
+        cases = cases[:3] if sys.argv[2] == "quick" else [cases[int(i)] for i in sys.argv[2].split(",")]
     worst = 0.0
     for c in cases:
         e, msg = run_case(backend, *c)
@@ -100,4 +123,4 @@ if __name__ == "__main__":
             sys.exit(2)
         worst = max(worst, e)
     print("worst", worst)
-    sys.exit(0 if worst < 1e-4 else 1)
+    sys.exit(0 if worst < (TF_TOL if backend == 2 else 1e-4) else 1)
