@@ -6,8 +6,11 @@
   torchrun ... bench.py --gpus N ...                        # one rank per GPU, weak scaling (32 utts / GPU)
 
 A "step" is one pass of the phoneme-id -> waveform hot path over one batch of synthetic ids.
-`value`   : whole-job audio-s/s with ids already in the job (device-resident result, no D2H).
-`e2e`     : same metric through the public call (`speak_batch_ids`): host ids in, host waveforms out.
+`value`   : whole-job audio-s/s, device-resident result (N > 1: incl. the NCCL id broadcast / length all-reduce).
+`e2e`     : same metric, host ids in -> host waveforms out: `speak_batch_ids` (N = 1) / `shard.Frontend` (N > 1: one
+            frontend on rank 0, results through a page-locked host segment shared by the ranks).
+`c5`      : BASELINE config 5 (1024 mixed-length utterances): aggregate audio-s/s and p50 / p99 completion latency.
+`secondary`: C1 (single 128-phoneme utterance) and C3 (high voice, 16 x 512) on the same box in the same run (N = 1).
 `roofline`: dominant kernel class (HiFi-GAN ResBlock convolutions), CUDA-event timed in the same run.
 `cpu_baseline`: the oracle (a port of the reference's onnxruntime graph) on this box's host cores.
 Prints ONE JSON line on rank 0.
@@ -162,6 +165,9 @@ def main():
     ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3"])
     ap.add_argument("--backend", type=int, default=int(os.environ.get("SB200_BACKEND", "1")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 mixed-length corpus")
+    ap.add_argument("--c5-utts", type=int, default=1024)
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C1 / C3 secondary lines (N = 1)")
     args = ap.parse_args()
 
     from sonata_b200 import workload
@@ -173,7 +179,8 @@ def main():
                             f"{B} x {NPH}-phoneme utterances per GPU, scales [0.667,1,0.8]",
                 "quality": quality, "batch_per_gpu": B, "phonemes": NPH, "ids_per_utt": 2 * NPH + 2,
                 "l2": "working set (>5 GB of activations per step) far exceeds the 126 MB L2",
-                "parallelism": f"dp{world}: independent utterance shards, one process per GPU, no data-path collective"}
+                "parallelism": (f"dp{world}: one process per GPU; rank 0 is the frontend (NCCL broadcast of ids, all-reduce of frame "
+                                "counts; utterances are independent, no collective on the waveform path)" if world > 1 else "dp1")}
     cores = os.cpu_count() or 1
 
     # ------------------------------------------------------------------ reference arm (CPU)
@@ -221,21 +228,18 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if rank == 0:
-        cfg_path = voicegen.write_voice(voicegen.default_voice_dir(), quality)
+        for q_ in {quality, "medium", "high"}:
+            voicegen.write_voice(voicegen.default_voice_dir(), q_)
     if world > 1:
         dist.barrier()
     cfg_path = voicegen.write_voice(voicegen.default_voice_dir(), quality)
     model = sonata_b200.from_config_path(cfg_path, device=local_rank)
     model.set_backend(args.backend)
+    lib = _native.lib()
 
     total_utts = B * world
     all_batches = [workload.synthetic_ids(NPH, utt=u) for u in range(total_utts)]
     ids_per_step = sum(len(b) for b in all_batches)
-    # this rank's shard: the same LPT partition `shard.scatter_ids` computes, evaluated locally (it is a pure function
-    # of the id counts), so the timed passes need no collective -- utterances are independent
-    my_idx = shard.lpt_partition([len(b) for b in all_batches], world)[rank] if world > 1 else list(range(total_utts))
-    local_batches = [all_batches[i] for i in my_idx]
-    lib = _native.lib()
 
     def barrier():
         torch.cuda.synchronize()
@@ -243,113 +247,166 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    out_cap = int(B * (2 * NPH + 2) * 8 * HOP)     # generous: 8 frames per id
-    d_out = torch.empty(out_cap, dtype=torch.float32, device="cuda") if world > 1 else None
+    def reduce_pair(wall, audio):
+        """max-over-ranks wall, sum-over-ranks audio"""
+        if world == 1:
+            return wall, audio
+        t = torch.tensor([wall, audio], dtype=torch.float64, device="cuda")
+        tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        return float(tm[0]), float(ts[1])
 
-    def step_device(utt_batches):
-        """device-resident pass; returns (audio_seconds_local, device_ms, job)"""
-        job = SynthesisJob(model, utt_batches)
-        ms = job.run()
-        frames, samples, _ = job.lengths()
-        return sum(samples) / SR, ms, job
+    # N > 1: ONE frontend (rank 0) holds every utterance; ids travel by NCCL broadcast, each rank runs its LPT shard, the
+    # frame counts are all-reduced, waveforms go device -> host into one page-locked segment shared by the ranks
+    # (sonata_b200/shard.py Frontend; SURVEY section 8e).  N = 1: the same public call without a process group.
+    fe = shard.Frontend(model) if world > 1 else None
+    if fe is not None:
+        fe.collect_profile = True
+
+    prof_acc = {}
+
+    def add_profile(regions):
+        for r in regions:
+            acc = prof_acc.setdefault(r["name"], {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+            for k in ("ms", "flops", "bytes", "launches"):
+                acc[k] += r[k]
+
+    def step_device(record):
+        """device-resident pass (results stay in HBM); returns this rank's (audio seconds, device ms)"""
+        if fe is None:
+            job = SynthesisJob(model, all_batches)
+            ms = job.run()
+            samples = job.lengths()[1]
+            if record:
+                add_profile(job.profile())
+            job.close()
+            return sum(samples) / SR, ms
+        fe.synthesize(all_batches if rank == 0 else None, device_only=True)
+        owner, samples = fe.last_table
+        if record:
+            add_profile(fe.last_profile)
+        return float(samples[owner == rank].sum()) / SR, fe.last_device_ms
+
+    def step_e2e():
+        """host ids in -> host waveforms out, through the public call (N = 1) / the one-frontend path (N > 1); returns
+        the audio seconds DELIVERED TO THE CALLER on this rank (all of it on rank 0 when N > 1)"""
+        if fe is None:
+            auds = model.infer_batch_with_values(all_batches)
+            return sum(len(a) for a in auds) / SR
+        out = fe.synthesize(all_batches if rank == 0 else None)
+        return sum(len(o) for o in out) / SR if rank == 0 else 0.0
 
     # warm-up (the clock sampler starts here so that nvidia-smi is already streaming when the timed region begins)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        _, _, j = step_device(local_batches)
-        j.close()
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        step_device(False)
 
-    prof_acc = {}
     barrier()
     launches0 = int(lib.sb200_launch_count())
     sampler.mark()
     t0 = time.perf_counter()
     audio_local, dev_ms = 0.0, 0.0
     for s in range(args.steps):
-        a_, ms, j = step_device(local_batches)
+        a_, ms = step_device(True)
         audio_local += a_; dev_ms += ms
-        for r in j.profile():
-            acc = prof_acc.setdefault(r["name"], {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
-            for k in ("ms", "flops", "bytes", "launches"):
-                acc[k] += r[k]
-        j.close()
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
     launches = int(lib.sb200_launch_count()) - launches0
-
-    t = torch.tensor([wall, audio_local, dev_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        wall_max, audio_total, dev_ms_max = float(tmax[0]), float(tsum[1]), float(tmax[2])
-    else:
-        wall_max, audio_total, dev_ms_max = wall, audio_local, dev_ms
+    wall_max, audio_total = reduce_pair(wall, audio_local)
+    dev_ms_max, _ = reduce_pair(dev_ms, 0.0)
     value = audio_total / wall_max
 
-    # ---------------- e2e: public call, host ids in -> host waveforms out ----------------
-    # Every rank serves its own batch through the public API (`infer_batch_with_values` = speak_batch on ids: ids from
-    # host memory, waveforms into pinned host memory).  The shards are independent -- no data-path collective -- so the
-    # whole-job number is the sum over ranks over the slowest rank's wall time.  The "one frontend on rank 0" variant
-    # (NCCL scatter of the ids, NCCL gather of the waveforms, one device->host copy on rank 0: `shard.py`) is timed
-    # separately below and reported as `e2e.frontend_rank0`; it funnels every GPU's audio through one PCIe link.
-    def step_e2e():
-        auds = model.infer_batch_with_values(local_batches)
-        return sum(len(a) for a in auds) / SR
-
-    pinned = {}
-
-    def step_frontend():
-        mine = shard.scatter_ids(all_batches if rank == 0 else None)
-        job = SynthesisJob(model, mine)
-        job.run(d_out.data_ptr(), out_cap)
-        _, samples, _ = job.lengths()
-        tot = int(sum(samples))
-        res = shard.gather_waveforms(d_out[:tot], samples, to_host=False)
-        job.close()
-        if rank != 0:
-            return 0.0
-        gl, owner, lens_all = res
-        n_audio = 0
-        for r_, g_ in enumerate(gl):
-            cnt = int(lens_all[owner == r_].sum())
-            if r_ not in pinned or pinned[r_].numel() < g_.numel():
-                pinned[r_] = torch.empty(g_.numel(), dtype=torch.float32, pin_memory=True)
-            pinned[r_][:cnt].copy_(g_[:cnt], non_blocking=True)
-            n_audio += cnt
-        torch.cuda.synchronize()
-        return n_audio / SR
-
-    step_e2e()
+    # ---------------- e2e ----------------
+    step_e2e(); step_e2e()
     barrier()
+    e2e_steps = max(args.steps, 10)
     t0 = time.perf_counter()
     e2e_audio = 0.0
-    e2e_steps = max(2, min(args.steps, 5))
     for _ in range(e2e_steps):
         e2e_audio += step_e2e()
     barrier()
-    e2e_wall = time.perf_counter() - t0
-    te = torch.tensor([e2e_wall, e2e_audio], dtype=torch.float64, device="cuda")
-    if world > 1:
-        tm = te.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        tsm = te.clone(); dist.all_reduce(tsm, op=dist.ReduceOp.SUM)
-        e2e_wall, e2e_audio = float(tm[0]), float(tsm[1])
+    e2e_wall, e2e_audio = reduce_pair(time.perf_counter() - t0, e2e_audio)
     e2e_value = e2e_audio / e2e_wall
     d2h_bytes = int(4 * e2e_audio * SR / e2e_steps)
-    frontend_value = None
+
+    # secondary (N > 1): every rank serves its own shard through the public call into its own pinned buffers
+    # (independent replicas, no frontend): the upper bound the one-frontend path is measured against
+    replicas_value = None
     if world > 1:
-        step_frontend()
+        my_idx = shard.lpt_partition([len(b) for b in all_batches], world)[rank]
+        local_batches = [all_batches[i] for i in my_idx]
+        model.infer_batch_with_values(local_batches)
         barrier()
         t0 = time.perf_counter()
-        fa = 0.0
-        for _ in range(2):
-            fa += step_frontend()
+        ra = 0.0
+        for _ in range(5):
+            ra += sum(len(a) for a in model.infer_batch_with_values(local_batches)) / SR
         barrier()
-        fw = time.perf_counter() - t0
-        tf_ = torch.tensor([fw, fa], dtype=torch.float64, device="cuda")
-        tm = tf_.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        frontend_value = float(tm[1]) / float(tm[0])
+        rw, ra = reduce_pair(time.perf_counter() - t0, ra)
+        replicas_value = ra / rw
+
+    # ---------------- C5: 1024 mixed-length utterances, all arriving at t = 0 (synth/src/benchmarks.rs:55-99) ----------------
+    # longest first, in waves of 32 utterances per GPU through the same e2e path; an utterance's latency is the time its
+    # wave's audio is in the frontend's hands
+    c5 = None
+    if quality == "medium" and not args.no_c5:
+        nph = workload.mixed_lengths(args.c5_utts)
+        c5_ids = [workload.synthetic_ids(int(n), utt=u) for u, n in enumerate(nph)]
+        waves = workload.length_buckets([len(x) for x in c5_ids], 32 * world)
+
+        def run_wave(w):
+            batch = [c5_ids[i] for i in w]
+            if fe is None:
+                return sum(len(a) for a in model.infer_batch_with_values(batch)) / SR
+            out = fe.synthesize(batch if rank == 0 else None)
+            return sum(len(o) for o in out) / SR if rank == 0 else 0.0
+        run_wave(waves[0]); run_wave(waves[-1])
+        barrier()
+        t0 = time.perf_counter()
+        done, audio = [], []
+        for w in waves:
+            audio.append(run_wave(w))
+            done.append(time.perf_counter() - t0)
+        barrier()
+        if rank == 0:
+            p50, p99, agg = workload.completion_stats(waves, done, audio)
+            c5 = {"workload": f"{args.c5_utts} utterances, N ~ U{{64..512}} phonemes (seed 7), longest first, waves of {32 * world}",
+                  "value": agg, "unit": "audio-s/s", "latency_p50_s": p50, "latency_p99_s": p99, "wall_s": done[-1],
+                  "audio_s": float(sum(audio)), "waves": len(waves)}
+
+    # ---------------- C1 / C3 as secondary lines (N = 1; same box, same run, own clock record) ----------------
+    secondary = {}
+    if world == 1 and args.workload == "C2" and not args.no_secondary:
+        for name in ("C1", "C3"):
+            q2, B2, N2 = workload.CONFIGS[name]
+            m2 = model if q2 == quality else sonata_b200.from_config_path(
+                voicegen.write_voice(voicegen.default_voice_dir(), q2), device=local_rank)
+            m2.set_backend(args.backend)
+            bt = [workload.synthetic_ids(N2, utt=u) for u in range(B2)]
+            steps2 = 30 if name == "C1" else 4
+            smp = ClockSampler(local_rank); smp.start()
+            for _ in range(3):
+                m2.infer_batch_with_values(bt)
+            torch.cuda.synchronize()
+            l0 = int(lib.sb200_launch_count())
+            smp.mark()
+            t0 = time.perf_counter(); a2 = 0.0
+            for _ in range(steps2):
+                a2 += sum(len(a) for a in m2.infer_batch_with_values(bt)) / SR
+            torch.cuda.synchronize()
+            w2 = time.perf_counter() - t0
+            l1 = int(lib.sb200_launch_count())
+            dms = 0.0
+            for _ in range(steps2):
+                j = SynthesisJob(m2, bt); dms += j.run(); j.close()
+            secondary[name] = {"workload": f"{name}: synthetic-{q2}, {B2} x {N2} phonemes", "e2e_audio_s_per_s": a2 / w2,
+                               "e2e_ms_per_step": 1e3 * w2 / steps2, "device_ms_per_step": dms / steps2,
+                               "launches_per_step": (l1 - l0) / steps2, "steps": steps2, "clocks": smp.stop()}
+            if m2 is not model:
+                m2.close()
 
     if rank == 0:
         peaks = read_peaks()
@@ -360,7 +417,7 @@ def main():
         all_ms = sum(v["ms"] for v in prof_acc.values())
         ach_gbs = mrf_bytes / (mrf_ms * 1e-3) / 1e9 if mrf_ms else 0.0
         roofline = {
-            "bound": "hbm", "kernel": ("conv_tc_kernel" if args.backend == 1 else "conv_simt_kernel") + " on dec.mrf* (HiFi-GAN ResBlock dilated Conv1d + residual; largest share of the step)",
+            "bound": "hbm", "kernel": ("conv_tc_kernel" if args.backend >= 1 else "conv_simt_kernel") + " on dec.mrf* (HiFi-GAN ResBlock dilated Conv1d + residual; largest share of the step)",
             "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"],
             "peak_source": f"{peaks['source']} (MEASURED_PEAKS.json hbm_gbs)" if peaks["source"] == "measured" else "fallback 6.65 TB/s",
             "traffic": ncu_traffic(),
@@ -383,24 +440,31 @@ def main():
             cpu_base = {"value": a_ / w_, "unit": "audio-s/s", "cores": threads, "kind": "port", "host_cpus": cores,
                         "sample": f"{n_s} utterances of the workload ({NPH} phonemes each), B=1 sequential like speak_batch, "
                                   f"PyTorch-CPU port of the reference graph, torch threads auto-tuned to {threads} of {cores}"}
+        backend_desc = {1: "tcgen05: bf16x2 split (flow, decoder) + chunk-flushed 3xTF32 (text encoder, duration predictor)",
+                        2: "tcgen05 bf16x2 (flow, decoder), fp32 CUDA cores (encoder, duration predictor)", 0: "fp32-simt"}[args.backend]
         line = {
             "metric": "audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * wall_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg_desc,
+            "warmup": W, "ms_per_step": 1e3 * wall_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 io; tcgen05 with split operands (2 x bf16 flow/decoder, 3 x tf32 encoder/predictor), fp32 accumulate",
+            "data": "synthetic", "config": cfg_desc,
             "device_ms_per_step": dev_ms_max / args.steps, "audio_s_per_step": audio_total / args.steps,
-            "backend": "tcgen05-bf16x2 (flow+decoder), fp32 CUDA cores (encoder, duration predictor)" if args.backend == 1 else "fp32-simt",
-            "clocks": clocks, "gpu_launches": launches,
+            "backend": backend_desc, "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(8 * ids_per_step),
                     "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
-                    "path": "per-rank public call (host ids -> pinned host waveforms), summed over ranks",
-                    "frontend_rank0": frontend_value},
-            "roofline": roofline, "regions": regions, "cpu_baseline": cpu_base,
+                    "path": ("public call speak_batch_ids: host ids -> pinned host waveforms" if world == 1 else
+                             "ONE frontend on rank 0: NCCL broadcast of the ids, per-rank batched pass, NCCL all-reduce of the frame "
+                             "counts, device->host copies into one page-locked host segment shared by the ranks"),
+                    "per_rank_replicas": replicas_value},
+            "roofline": roofline, "regions": regions, "cpu_baseline": cpu_base, "c5": c5, "secondary": secondary or None,
         }
         sys.stdout.flush()
         os.dup2(_stdout_fd, 1)
         print(json.dumps(line), flush=True)
         sys.stdout.flush()
         os.dup2(2, 1)
+    if fe is not None:
+        fe.close()
     model.close()
     if world > 1:
         dist.barrier()

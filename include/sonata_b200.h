@@ -134,6 +134,18 @@ size_t sb200_job_batch(const sb200_job* job);
 int32_t sb200_job_fetch_i16(sb200_job* job, int16_t** outs, size_t* lens, sb200_error* err);
 void sb200_i16_free(int16_t* p);
 int32_t sb200_job_lengths(const sb200_job* job, int64_t* frames, int64_t* samples, int64_t* out_offsets);
+/* Copy the result of a finished job into CALLER-OWNED host memory, utterances back to back in batch order.
+ * format 0: f32 samples (what infer_with_values returns, piper/src/lib.rs:382-392);
+ * format 1: i16 PCM, peak-normalised per utterance on the device (= AudioSamples::to_i16_vec, samples.rs:51-75;
+ *           what libsonata hands to its callback, capi/src/lib.rs:416-438) -- half the device->host bytes.
+ * `dst` may be ordinary or page-locked memory (see sb200_host_register), e.g. a slice of a segment shared by the
+ * per-GPU worker processes of one frontend.  *written = bytes written; fails if `capacity_bytes` is too small. */
+int32_t sb200_job_copy_out(sb200_job* job, void* dst, size_t capacity_bytes, int32_t format, size_t* written,
+                           sb200_error* err);
+/* Page-lock / unlock caller memory for DMA (cudaHostRegister) so that hosts without CUDA bindings (Rust, ctypes)
+ * can pin a result segment once and reuse it.  Returns 0 on success. */
+int32_t sb200_host_register(void* ptr, size_t bytes, sb200_error* err);
+int32_t sb200_host_unregister(void* ptr);
 void sb200_job_free(sb200_job* job);
 
 /* ---- streaming: VitsStreamingModel (piper/src/lib.rs:480-669) ----

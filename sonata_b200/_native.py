@@ -74,6 +74,9 @@ SIGNATURES = {
     "sb200_i16_free": (None, [C.POINTER(C.c_int16)]),
     "sb200_job_batch": (C.c_size_t, [_P]),
     "sb200_job_lengths": (C.c_int32, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "sb200_job_copy_out": (C.c_int32, [_P, C.c_void_p, C.c_size_t, C.c_int32, C.POINTER(C.c_size_t), _ERR]),
+    "sb200_host_register": (C.c_int32, [C.c_void_p, C.c_size_t, _ERR]),
+    "sb200_host_unregister": (C.c_int32, [C.c_void_p]),
     "sb200_job_free": (None, [_P]),
     "sb200_encode_ids": (C.c_int32, [_P, C.POINTER(C.c_int64), C.c_size_t, C.POINTER(_P), _ERR]),
     "sb200_latent_frames": (C.c_int64, [_P]),

@@ -256,6 +256,49 @@ int32_t sb200_job_fetch_i16(sb200_job* job, int16_t** outs, size_t* lens, sb200_
     });
 }
 void sb200_i16_free(int16_t* p) { free(p); }
+
+int32_t sb200_job_copy_out(sb200_job* job, void* dst, size_t cap, int32_t format, size_t* written, sb200_error* err) {
+    return guarded(err, [&] {
+        Job& j = *job->j;
+        if (!j.ran || j.encode_only) throw Error(19, "job has not produced audio");
+        if (!dst) throw Error(19, "null destination");
+        Voice& v = *j.v;
+        SB_CUDA(cudaSetDevice(v.device));
+        cudaStream_t st = j.ctx->stream;
+        const size_t n = (size_t)j.total_samples;
+        const size_t bytes = n * (format == 1 ? 2 : 4);
+        if (bytes > cap) throw Error(19, "destination buffer is too small for the synthesis result");
+        if (format == 1) {
+            const int hop = v.a.hop();
+            long long mx = 0;
+            for (size_t b = 0; b < j.B; b++) mx = std::max<long long>(mx, (long long)j.y_len[b] * hop);
+            short* d_i16 = nullptr; unsigned* d_max = nullptr;
+            SB_CUDA(cudaMallocAsync(&d_i16, n * 2 + 16, st));
+            SB_CUDA(cudaMallocAsync(&d_max, sizeof(unsigned) * j.B, st));
+            launch_i16(j.d_wav, j.d_fsegs, (int)j.B, hop, mx, d_max, d_i16, st);
+            cudaError_t e = cudaMemcpyAsync(dst, d_i16, bytes, cudaMemcpyDeviceToHost, st);
+            cudaFreeAsync(d_i16, st);
+            cudaFreeAsync(d_max, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) throw Error(19, std::string("CUDA error: ") + cudaGetErrorString(e));
+        } else {
+            SB_CUDA(cudaMemcpyAsync(dst, j.d_wav, bytes, cudaMemcpyDeviceToHost, st));
+            SB_CUDA(cudaStreamSynchronize(st));
+        }
+        if (written) *written = bytes;
+    });
+}
+int32_t sb200_host_register(void* ptr, size_t bytes, sb200_error* err) {
+    return guarded(err, [&] {
+        const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+        if (e != cudaSuccess) { cudaGetLastError(); throw Error(19, std::string("cudaHostRegister failed: ") + cudaGetErrorString(e)); }
+    });
+}
+int32_t sb200_host_unregister(void* ptr) {
+    const cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) cudaGetLastError();
+    return e == cudaSuccess ? 0 : 19;
+}
 size_t sb200_job_batch(const sb200_job* job) { return job->j->B; }
 int32_t sb200_job_lengths(const sb200_job* job, int64_t* frames, int64_t* samples, int64_t* out_offsets) {
     const Job& j = *job->j;

@@ -77,6 +77,14 @@ class SynthesisJob:
             self._lib.sb200_i16_free(outs[i])
         return res
 
+    def copy_out(self, dst_address: int, capacity_bytes: int, fmt: int = 0) -> int:
+        """Device -> host copy of the whole result (utterances back to back) into caller memory, e.g. a slice of the
+        host segment shared by the ranks of one frontend; fmt 0 = f32, 1 = peak-normalised i16 PCM.  Returns bytes."""
+        wr, err = C.c_size_t(), N.sb200_error()
+        _check(self._lib.sb200_job_copy_out(self._h, C.c_void_p(dst_address), capacity_bytes, fmt, C.byref(wr),
+                                            C.byref(err)), err)
+        return int(wr.value)
+
     def lengths(self):
         f = (C.c_int64 * self.batch)()
         s = (C.c_int64 * self.batch)()

@@ -2,11 +2,15 @@
 
 Utterances are independent (the reference already treats sentences as independent tasks,
 synth/src/lib.rs:316-320), so the path shards with NO data-path collective: the only exchanges are
-the ragged scatter of ids from rank 0 and the ragged gather of waveforms back to rank 0, done with
-torch.distributed (NCCL over NVLink on GPUs; gloo in the CPU tests).  Weights are replicated.
+the scatter of ids from rank 0 and the collection of waveforms at rank 0, done with torch.distributed (NCCL over
+NVLink on GPUs; gloo in the CPU tests).  Weights are replicated.  `Frontend` is the production path (ids broadcast,
+results through a page-locked host segment shared by the ranks); `scatter_ids` / `gather_waveforms` keep the plain
+NCCL scatter / gather into rank 0's HBM for comparison.
 """
 from __future__ import annotations
 
+import ctypes as C
+import os
 from typing import Callable, List, Optional, Sequence
 
 import numpy as np
@@ -111,92 +115,205 @@ def gather_waveforms(local_wave: torch.Tensor, local_lens: Sequence[int], group=
     return None
 
 
-class HostGather:
-    """Gather into ONE host buffer without funnelling every GPU's audio through rank 0's PCIe link.
-
-    A POSIX shared-memory segment (grown on demand, reused across calls) is mapped by every rank; each rank copies its
-    own waveforms device->host into its slice -- N links in parallel -- and rank 0 reads all of them from the same
-    pages.  The collectives carry only the length table and the segment's name.  With `pin=True` on a CUDA build the
-    mapping is page-locked (`cudaHostRegister`) so the copies are DMA transfers.  (NCCL gather + one copy reached
-    80k audio-s/s at N = 8 where per-rank host buffers reach 174k: profiles/notes_r01.md.)
-    """
+class SharedSegment:
+    """A host memory segment mapped by every rank of the box (file-backed MAP_SHARED mapping on a RAM filesystem when
+    one has room, else the temp directory), optionally page-locked through the library (`sb200_host_register`) so
+    device->host copies into it are DMA transfers.  Grown on demand; the name travels over the process group."""
 
     def __init__(self, group=None, pin: bool = True):
         self.group, self.pin = group, pin
-        self.shm = None
-        self.cap = 0
-        self._registered = None
+        self.path, self.mm, self.cap, self._fd = None, None, 0, None
+        self._reg_ptr, self._np = None, None
 
-    def _ensure(self, nbytes: int):
-        from multiprocessing import shared_memory
-        rank = dist.get_rank(self.group)
-        need = torch.tensor([int(nbytes > self.cap)], dtype=torch.int64, device=_dev(self.group))
-        dist.all_reduce(need, op=dist.ReduceOp.MAX, group=self.group)
-        if int(need.item()) == 0:
+    @staticmethod
+    def _pick_dir(nbytes: int) -> str:
+        import tempfile
+        for d in ("/dev/shm", tempfile.gettempdir()):
+            try:
+                st = os.statvfs(d)
+                if st.f_bavail * st.f_frsize > nbytes + (64 << 20):
+                    return d
+            except OSError:
+                continue
+        return tempfile.gettempdir()
+
+    def ensure(self, nbytes: int) -> None:
+        """collective: every rank calls with the same `nbytes`"""
+        if nbytes <= self.cap:
             return
-        self.close(unlink=rank == 0)
+        import mmap
+        rank = dist.get_rank(self.group)
+        self.close()
         cap = max(int(nbytes * 1.25), 1 << 20)
+        cap = (cap + 4095) & ~4095
         name = [None]
         if rank == 0:
-            self.shm = shared_memory.SharedMemory(create=True, size=cap)
-            name[0] = self.shm.name
+            import tempfile
+            fd, path = tempfile.mkstemp(prefix="sb200_seg_", dir=self._pick_dir(cap))
+            os.ftruncate(fd, cap)
+            name[0] = path
+            self._fd = fd
         dist.broadcast_object_list(name, src=0, group=self.group)
+        self.path = name[0]
         if rank != 0:
-            self.shm = shared_memory.SharedMemory(name=name[0])
+            self._fd = os.open(self.path, os.O_RDWR)
+        self.mm = mmap.mmap(self._fd, cap, mmap.MAP_SHARED, mmap.PROT_READ | mmap.PROT_WRITE)
+        self._np = np.frombuffer(self.mm, dtype=np.uint8)
         self.cap = cap
-        if self.pin and torch.cuda.is_available() and dist.get_backend(self.group) == "nccl":
-            buf = np.frombuffer(self.shm.buf, dtype=np.uint8)
-            if int(torch.cuda.cudart().cudaHostRegister(buf.ctypes.data, cap, 0)) == 0:
-                self._registered = buf.ctypes.data     # on failure the copies still work, through pageable memory
+        if self.pin:
+            try:
+                from . import _native as N
+                lib = N.lib()
+                if int(lib.sb200_device_count()) > 0:
+                    err = N.sb200_error()
+                    if int(lib.sb200_host_register(self._np.ctypes.data, cap, C.byref(err))) == 0:
+                        self._reg_ptr = self._np.ctypes.data
+                    elif err.message:
+                        lib.sb200_string_free(err.message)     # copies still work, through pageable memory
+            except ImportError:
+                pass
         dist.barrier(group=self.group)
+        if rank == 0:
+            os.unlink(self.path)          # every rank holds its mapping; the name is no longer needed
 
-    def gather(self, local_wave: torch.Tensor, local_lens: Sequence[int]):
-        """Same contract as `gather_waveforms(..., to_host=True)`: rank 0 returns the waveforms in GLOBAL utterance
-        order (views into the shared segment, valid until the next call), other ranks return None."""
+    @property
+    def address(self) -> int:
+        return self._np.ctypes.data
+
+    def view(self, offset: int, nbytes: int, dtype) -> np.ndarray:
+        return self._np[offset:offset + nbytes].view(dtype)
+
+    def close(self) -> None:
+        if self.mm is None:
+            return
+        if self._reg_ptr is not None:
+            from . import _native as N
+            N.lib().sb200_host_unregister(self._reg_ptr)
+            self._reg_ptr = None
+        self._np = None
+        try:
+            self.mm.close()
+        except BufferError:
+            pass                                   # views handed out earlier are still alive
+        if self._fd is not None:
+            os.close(self._fd)
+        self.mm, self.cap, self._fd = None, 0, None
+
+
+class Frontend:
+    """ONE frontend process (rank 0) serving a batch of utterances on every GPU of the box: the multi-GPU form of
+    `SonataSpeechStreamParallel::new` (synth/src/lib.rs:314-325: fan the sentences out, collect every result).
+
+      rank 0 : ids of all utterances  --NCCL broadcast (ids + LPT owner table, ~1 MB)-->  every rank
+      rank r : its shard as ONE batched pass on its GPU (weights replicated)
+      all    : per-utterance sample counts  --NCCL all-reduce (n int64)-->  exact layout of the result segment
+      rank r : device -> host copy of its waveforms straight into ITS SLICE of a page-locked host segment shared by
+               all ranks -- N PCIe links in parallel instead of funnelling every GPU's audio through rank 0
+               (NCCL gather + one copy: 80k audio-s/s at N = 8 against 174k for per-rank buffers, profiles/notes_r01.md)
+      rank 0 : after a barrier, reads every waveform from the same pages (zero-copy numpy views)
+
+    `pcm16=True` delivers peak-normalised i16 PCM converted on the device (`to_i16_vec`, samples.rs:51-75): what
+    libsonata's callback receives, at half the device->host bytes.  Every device / host buffer is allocated once and
+    reused; the collectives carry only ids and length tables.  `run_local(ids_list, dst, capacity, fmt)` is the per-rank
+    synthesis hook (default: the CUDA job of `model`); the gloo tests pass a deterministic stand-in."""
+
+    def __init__(self, model=None, group=None, pcm16: bool = False, pin: bool = True, run_local: Optional[Callable] = None):
+        self.model, self.group, self.pcm16 = model, group, pcm16
+        self.seg = SharedSegment(group, pin)
+        self.run_local = run_local
+        self._payload = None           # device buffer for the id broadcast
+        self._lens = None              # device buffer for the sample-count all-reduce
+        self.last_device_ms = 0.0
+        self.last_table = None
+        self.collect_profile = False   # keep the per-region device times of the last local pass (bench.py)
+        self.last_profile = []
+
+    # -- collective plumbing ----------------------------------------------------------------------------------------
+    def _bcast_ids(self, batches):
         rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
         dev = _dev(self.group)
-        info = scatter_ids.last
-        n, owner, mine = info["n"], info["owner"], info["mine"]
-        lens = torch.zeros(n, dtype=torch.int64, device=dev)
+        meta = torch.zeros(2, dtype=torch.int64, device=dev)
+        if rank == 0:
+            lens = np.array([len(b) for b in batches], dtype=np.int64)
+            owner = np.zeros(len(batches), dtype=np.int64)
+            for r, p in enumerate(lpt_partition(lens.tolist(), world)):
+                owner[p] = r
+            flat = np.concatenate([lens, owner] + [np.asarray(b, dtype=np.int64) for b in batches])
+            meta = torch.tensor([len(batches), flat.size], dtype=torch.int64).to(dev)
+        dist.broadcast(meta, 0, group=self.group)
+        n, total = (int(x) for x in meta.cpu().tolist())
+        if self._payload is None or self._payload.numel() < total:
+            self._payload = torch.empty(max(int(total * 1.5), 1 << 16), dtype=torch.int64, device=dev)
+        buf = self._payload[:total]
+        if rank == 0:
+            buf.copy_(torch.from_numpy(flat))
+        dist.broadcast(buf, 0, group=self.group)
+        flat = buf.cpu().numpy()
+        lens, owner = flat[:n], flat[n:2 * n]
+        offs = 2 * n + np.concatenate([[0], np.cumsum(lens)])
+        mine = np.nonzero(owner == rank)[0]
+        return n, owner, mine, [flat[offs[i]:offs[i + 1]] for i in mine]
+
+    def synthesize(self, batches: Optional[Sequence[np.ndarray]], device_only: bool = False):
+        """Collective.  Rank 0 passes every utterance's ids and gets the waveforms back in utterance order (views into
+        the shared segment, valid until the next call); the other ranks pass None and get None.
+        `device_only`: stop after the passes (results stay in each GPU's memory): the device-resident timing of bench.py."""
+        rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        dev = _dev(self.group)
+        n, owner, mine, my_ids = self._bcast_ids(batches)
+        bps = 2 if self.pcm16 else 4
+        fmt = 1 if self.pcm16 else 0
+        # two-step because the layout of the segment depends on every rank's frame counts: run first (waveforms stay on
+        # the device), exchange the counts, then copy out.  The job stays alive in between.
+        job = None
+        if self.run_local is None and self.model is not None:
+            from .job import SynthesisJob
+            samples_local = []
+            if my_ids:
+                job = SynthesisJob(self.model, my_ids)
+                self.last_device_ms = job.run()
+                samples_local = job.lengths()[1]
+                if self.collect_profile:
+                    self.last_profile = job.profile()
+        else:
+            samples_local = self.run_local(my_ids, None, 0, fmt) if my_ids else []
+        if self._lens is None or self._lens.numel() < n:
+            self._lens = torch.zeros(max(n, 1024), dtype=torch.int64, device=dev)
+        lens_t = self._lens[:n]
+        lens_t.zero_()
         if len(mine):
-            lens[torch.from_numpy(mine).to(dev)] = torch.tensor(list(local_lens), dtype=torch.int64, device=dev)
-        dist.all_reduce(lens, group=self.group)
-        lens_all = lens.cpu().numpy()
-        offs = np.zeros(n + 1, dtype=np.int64)
-        order = [i for r in range(world) for i in np.nonzero(owner == r)[0]]      # rank-major layout of the segment
+            lens_t[torch.from_numpy(mine).to(dev)] = torch.tensor(list(samples_local), dtype=torch.int64).to(dev)
+        dist.all_reduce(lens_t, group=self.group)
+        samples = lens_t.cpu().numpy()
+        self.last_table = (owner, samples)
+        if device_only:
+            if job is not None:
+                job.close()
+            return None
+        order = [i for r in range(world) for i in np.nonzero(owner == r)[0]]      # rank-major: a rank's slice is contiguous
+        offs = np.zeros(n, dtype=np.int64)
         pos = 0
         for i in order:
             offs[i] = pos
-            pos += int(lens_all[i])
-        self._ensure(pos * 4)
-        seg = np.frombuffer(self.shm.buf, dtype=np.float32, count=self.cap // 4)
-        my_tot = int(lens_all[mine].sum()) if len(mine) else 0
-        if my_tot:
-            start = int(offs[mine[0]])                                            # a rank's utterances are contiguous
-            torch.from_numpy(seg[start:start + my_tot]).copy_(local_wave[:my_tot])
-        if dev.type == "cuda":
-            torch.cuda.synchronize()
+            pos += int(samples[i]) * bps
+        self.seg.ensure(max(pos, 1))
+        my_bytes = int(samples[mine].sum()) * bps if len(mine) else 0
+        if my_bytes:
+            start = int(offs[mine[0]])
+            if job is not None:
+                job.copy_out(self.seg.address + start, my_bytes, fmt)
+            else:
+                self.run_local(my_ids, self.seg.view(start, my_bytes, np.int16 if self.pcm16 else np.float32), my_bytes, fmt)
+        if job is not None:
+            job.close()
         dist.barrier(group=self.group)
         if rank != 0:
             return None
-        return [seg[int(offs[i]):int(offs[i]) + int(lens_all[i])] for i in range(n)]
+        dt = np.int16 if self.pcm16 else np.float32
+        return [self.seg.view(int(offs[i]), int(samples[i]) * bps, dt) for i in range(n)]
 
-    def close(self, unlink: bool = False):
-        if self.shm is None:
-            return
-        if self._registered is not None:
-            torch.cuda.cudart().cudaHostUnregister(self._registered)
-            self._registered = None
-        try:
-            self.shm.close()
-        except BufferError:
-            pass                                   # views handed out by gather() are still alive
-        if unlink:
-            try:
-                self.shm.unlink()
-            except FileNotFoundError:
-                pass
-        self.shm, self.cap = None, 0
+    def close(self):
+        self.seg.close()
 
 
 def sharded_synthesize(batches: Optional[Sequence[np.ndarray]], synth: Callable[[List[np.ndarray]], List[np.ndarray]],

@@ -192,45 +192,55 @@ def _gloo_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def _gloo_worker_shm(rank, world, port, q):
+def _gloo_worker_frontend(rank, world, port, q):
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from sonata_b200 import shard, workload
-    hg = shard.HostGather(pin=False)
     ok = True
-    for rnd, lens in enumerate(([5, 17, 3, 9, 12, 1, 8], [40, 2], [3, 3, 3, 3, 3, 3, 3, 3, 900])):   # the third round grows the segment
-        batches = [workload.synthetic_ids(n, utt=10 * rnd + i) for i, n in enumerate(lens)]
-        mine = shard.scatter_ids(batches if rank == 0 else None)
-        waves = [np.repeat(ids.astype(np.float32), 3) + rnd for ids in mine]
-        local = torch.from_numpy(np.concatenate(waves)) if waves else torch.zeros(0)
-        out = hg.gather(local, [len(w) for w in waves])
-        if rank == 0:
-            ok = ok and len(out) == len(batches) and all(
-                np.array_equal(o, np.repeat(b.astype(np.float32), 3) + rnd) for o, b in zip(out, batches))
-        else:
-            ok = ok and out is None
-        del out
+    for pcm16 in (False, True):
+        def fake(ids_list, dst, cap, fmt, pcm16=pcm16):       # deterministic stand-in for the CUDA pass: 3 samples per id
+            waves = [(np.repeat(ids.astype(np.float32), 3) % 100).astype(np.int16 if pcm16 else np.float32) for ids in ids_list]
+            if dst is not None:
+                flat = np.concatenate(waves)
+                assert flat.nbytes == cap and fmt == (1 if pcm16 else 0)
+                dst[:] = flat
+            return [len(w) for w in waves]
+        fe = shard.Frontend(group=None, pcm16=pcm16, pin=False, run_local=fake)
+        for rnd, lens in enumerate(([5, 17, 3, 9, 12, 1, 8], [40, 2], [3, 3, 3, 3, 3, 3, 3, 3, 400000])):   # round 3 grows the segment
+            batches = [workload.synthetic_ids(n, utt=10 * rnd + i) for i, n in enumerate(lens)]
+            out = fe.synthesize(batches if rank == 0 else None)
+            if rank == 0:
+                dt = np.int16 if pcm16 else np.float32
+                ok = ok and len(out) == len(batches) and all(
+                    o.dtype == dt and np.array_equal(o, (np.repeat(b.astype(np.float32), 3) % 100).astype(dt)) for o, b in zip(out, batches))
+                owner, samples = fe.last_table
+                ok = ok and sorted(set(owner.tolist())) == [0, 1] and samples.tolist() == [3 * len(b) for b in batches]
+            else:
+                ok = ok and out is None
+            del out
+        ok = ok and fe.synthesize([workload.synthetic_ids(4)] if rank == 0 else None, device_only=True) is None
+        fe.close()
     dist.barrier()
-    hg.close(unlink=rank == 0)
     if rank == 0:
         q.put(bool(ok))
     dist.destroy_process_group()
 
 
-def test_host_gather_shared_segment_gloo_world2():
-    """`shard.HostGather`: every rank writes its waveforms into one shared host segment (no funnel through rank 0)."""
+def test_frontend_shared_segment_gloo_world2():
+    """`shard.Frontend`: rank 0 broadcasts the ids, every rank writes its waveforms (f32 or i16) into its slice of one
+    shared host segment, rank 0 reads them in utterance order; the segment grows on demand and is reused."""
     import socket
     import torch.multiprocessing as mp
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_gloo_worker_shm, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_gloo_worker_frontend, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
-        p.join(120)
+        p.join(180)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
 
