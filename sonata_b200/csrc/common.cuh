@@ -54,6 +54,27 @@ struct ConvArgs {
     const float* res; int ldres;
     float* y0; int ldy0; int acc0; int split;                     // columns [0, split)
     float* y1; int ldy1; int acc1;                                // columns [split, cout)
+    float* yt; int yt_col0; int ldyt;                             // conv_tf.cu: column tiles >= yt_col0 are stored TRANSPOSED,
+                                                                  // yt[(n - yt_col0) * ldyt + q] (row index contiguous)
+};
+
+// One tile of a grouped GEMM on conv_tf.cu's kernel (the attention contractions): two 128-row m-tiles of A against
+// one block of nth B rows over `nkb` 32-column K-blocks;  C = scale * A . B^T (+ res).
+struct TfTile {
+    int a_row0[2];        // first row of m-tile h in A (rows outside the array read as zeros)
+    int a_col0;           // first K column in A
+    int b_row0;           // first row of the B block
+    int b_col0;           // first K column in B
+    int nkb;              // 32-column K-blocks
+    int rows_valid[2];    // rows of m-tile h that are stored
+    long long out_off[2]; // element offset of (row 0, column 0) of m-tile h's output block in y (and res)
+};
+struct TfGemm {
+    const float* a; int a_rows, a_cols, lda;      // A [a_rows][a_cols], K along the columns
+    const float* b; int b_rows, b_cols, ldb;      // B [b_rows][b_cols], rows = output columns
+    int nth;                                      // B rows (= output columns) per tile: 96 / 64 / 32
+    float* y; int ldy; const float* res; float scale;
+    const TfTile* tiles; int ntiles;              // device table
 };
 
 // Function attributes (opt-in shared-memory size) are per DEVICE: `run` executes `f` the first time the calling site
@@ -87,11 +108,16 @@ bool conv_tf_supported(const ConvArgs& a);
 void launch_conv_tf(const ConvArgs& a, cudaStream_t st);
 size_t conv_tf_weight_floats(int cin, int cout, int ntaps);
 void conv_tf_build_weights(const float* wt, int ldw, int cin, int cout, int ntaps, float* out);
+bool gemm_tf_supported(const TfGemm& g);
+void launch_gemm_tf(const TfGemm& g, cudaStream_t st);
+void throw_launch_error(const char* what);
 bool conv_ts_supported(const ConvArgs& a);
 void launch_conv_ts(const ConvArgs& a, cudaStream_t st);
 size_t conv_ts_weight_floats(int ntaps);
 void conv_ts_build_weights(const float* wt, int ldw, int ntaps, float* out);
       // column tile the SIMT kernel will use for this cout (for weight padding)
+
+struct SegInfo { int off; int len; };   // rows
 
 // ---- misc kernels (kernels_misc.cu) ----
 void launch_embed(const int* ids_rows, const float* emb, float scale, float* x, int rows, int H, cudaStream_t st);
@@ -101,7 +127,10 @@ void launch_ln(const float* x, const float* res1, const float* res2, const float
 // out = GELU(LN(depthwise_conv_k(x, dilation)))   (DDSConv first half)
 void launch_dw_ln_gelu(const float* x, const float* wdw /*[k][C]*/, const float* bdw, int k, int dil,
                        const float* gamma, const float* beta, float* out, int C, RowMap map, cudaStream_t st);
-struct SegInfo { int off; int len; };   // rows
+// Relative-position softmax between the two attention GEMMs (in place on the score rows): see kernels_misc.cu
+void launch_attn_softmax(float* S, int Tp, const float* qkv, int ldq, const float* relk, const float* relv, int window,
+                         float* orel, int ldo, int H, int heads, int RX, const SegInfo* segs, const int* seg_of_gran,
+                         int gran, int max_len, cudaStream_t st);
 void launch_attention(const float* qkv, int ldq, const float* relk, const float* relv, int window,
                       float* out, int ldo, int H, int heads, const SegInfo* segs, int nseg, int max_len,
                       cudaStream_t st);

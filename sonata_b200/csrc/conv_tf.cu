@@ -25,6 +25,11 @@
 //     bias / ReLU / residual / scale / accumulate and 256-bit row-per-thread stores.
 // Warps: w0/w1 MMA issuers (w0 allocates TMEM), w2 weight loader, w3 activation loader, w4-5 converters,
 // w6-9 / w10-13 epilogue groups of issuer 0 / 1.  Every mbarrier wait carries the watchdog of tc_common.cuh.
+//
+// GM = 1 instantiation ("grouped GEMM", the two contractions of the relative-position attention): the B operand is
+// not a pre-split weight image but a second ACTIVATION matrix (K for Q.K^T, V^T for P.V), fetched by TMA tensor loads
+// and split by the converter warps like A; tiles come from a host-built table (one entry per (utterance, head,
+// m-tile pair, n-tile) with its own K extent), so ragged batches need no padding.  Four converter warps (16 warps).
 #include "tc_common.cuh"
 #include <stdlib.h>
 #include <string.h>
@@ -35,9 +40,12 @@ namespace {
 
 using namespace tcx;
 
-constexpr int TF_THREADS = 448;
-constexpr int TF_WARP_WLOAD = 2, TF_WARP_ALOAD = 3, TF_WARP_CONV0 = 4, TF_WARP_EPI0 = 6;
-constexpr int TF_NCONV = 64;                 // converter threads
+constexpr int TF_WARP_WLOAD = 2, TF_WARP_ALOAD = 3, TF_WARP_CONV0 = 4;
+template <int GM> struct TfCfg {
+    static constexpr int NCONV = GM ? 128 : 64;                    // converter threads
+    static constexpr int WARP_EPI0 = TF_WARP_CONV0 + NCONV / 32;   // first epilogue warp
+    static constexpr int THREADS = (WARP_EPI0 + 8) * 32;
+};
 constexpr int TF_NA_MAX = 4, TF_NW_MAX = 8;
 constexpr int TF_NTH_MAX = 96;
 
@@ -69,8 +77,13 @@ __device__ __forceinline__ float tf32_rn(float v) {
     return __uint_as_float(r);
 }
 
-__global__ void __launch_bounds__(TF_THREADS, 1) conv_tf_kernel(const ConvArgs a, const TfLaunch L,
-                                                                 const __grid_constant__ CUtensorMap tm_x) {
+template <int GM>
+__global__ void __launch_bounds__(TfCfg<GM>::THREADS, 1) conv_tf_kernel(const ConvArgs a, const TfLaunch L,
+                                                                         const __grid_constant__ CUtensorMap tm_x,
+                                                                         const __grid_constant__ CUtensorMap tm_b,
+                                                                         const TfTile* __restrict__ tiles) {
+    constexpr int TF_NCONV = TfCfg<GM>::NCONV;
+    constexpr int TF_WARP_EPI0 = TfCfg<GM>::WARP_EPI0;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t a_img = (uint32_t)L.win * 128u;               // one image (hi or lo) of a window
@@ -85,15 +98,19 @@ __global__ void __launch_bounds__(TF_THREADS, 1) conv_tf_kernel(const ConvArgs a
     uint64_t* a_empty = a_full + 2 * TF_NA_MAX;                  // [2][TF_NA_MAX]
     uint64_t* acc_full = a_empty + 2 * TF_NA_MAX;                // [2][2]
     uint64_t* acc_empty = acc_full + 4;                          // [2][2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 4);
+    uint64_t* wraw_full = acc_empty + 4;                         // [TF_NW_MAX]  GM: B operand landed (TMA), not yet split
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wraw_full + TF_NW_MAX);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nkb = a.cin / 32;
-    const int total_tiles = L.ntiles_mp * L.ntiles_n;
+    const int nkb_conv = a.cin / 32;
+    const int total_tiles = GM ? L.ntiles_mp : L.ntiles_mp * L.ntiles_n;
+    auto tile_nkb = [&](int tl) -> int { return GM ? tiles[(int)blockIdx.x + tl * (int)gridDim.x].nkb : nkb_conv; };
     const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (tid == 0) {
-        for (int s = 0; s < TF_NW_MAX; s++) { mbar_init(smem_u32(&w_full[s]), 1); mbar_init(smem_u32(&w_empty[s]), 2); }
+        for (int s = 0; s < TF_NW_MAX; s++) {
+            mbar_init(smem_u32(&w_full[s]), GM ? TF_NCONV : 1); mbar_init(smem_u32(&w_empty[s]), 2); mbar_init(smem_u32(&wraw_full[s]), 1);
+        }
         for (int s = 0; s < 2 * TF_NA_MAX; s++) {
             mbar_init(smem_u32(&raw_full[s]), 1); mbar_init(smem_u32(&a_full[s]), TF_NCONV); mbar_init(smem_u32(&a_empty[s]), 1);
         }
@@ -118,6 +135,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) conv_tf_kernel(const ConvArgs a
         const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
         int li = 0, lw = 0, lc = 0;            // activation-stage, weight-stage and chunk counters
         for (int tl = 0; tl < my_tiles; tl++) {
+            const int nkb = tile_nkb(tl);
             for (int kb = 0; kb < nkb; kb++, li++) {
                 const int cpos = kb % L.chunk_kb;
                 const int st = lc & 1;
@@ -164,8 +182,20 @@ __global__ void __launch_bounds__(TF_THREADS, 1) conv_tf_kernel(const ConvArgs a
         }
     } else if (warp == TF_WARP_WLOAD) {
         // ===================== weight loader: one bulk copy per (K-block, tap) stage =====================
-        if (lane == 0) {
-            const int per_tile = nkb * a.ntaps;
+        if (lane == 0 && GM) {
+            // B operand = activations: one TMA tensor load (32 K-columns x nth rows) per K-block into the hi image slot
+            int lw = 0;
+            for (int tl = 0; tl < my_tiles; tl++) {
+                const TfTile T = tiles[(int)blockIdx.x + tl * (int)gridDim.x];
+                for (int kb = 0; kb < T.nkb; kb++, lw++) {
+                    const int ws = lw % L.nw;
+                    mbar_wait(smem_u32(&w_empty[ws]), (uint32_t)(((lw / L.nw) & 1) ^ 1));
+                    mbar_expect_tx(smem_u32(&wraw_full[ws]), w_img);
+                    tma_load_2d(smem_u32(W0 + (size_t)ws * 2 * w_img), &tm_b, smem_u32(&wraw_full[ws]), T.b_col0 + kb * 32, T.b_row0);
+                }
+            }
+        } else if (lane == 0) {
+            const int per_tile = nkb_conv * a.ntaps;
             const uint32_t w_stage = 2 * w_img;
             int lw = 0;
             for (int tl = 0; tl < my_tiles; tl++) {
@@ -188,13 +218,17 @@ __global__ void __launch_bounds__(TF_THREADS, 1) conv_tf_kernel(const ConvArgs a
             for (int tl = 0; tl < my_tiles; tl++) {
                 const int tg = (int)blockIdx.x + tl * (int)gridDim.x;
                 const int mp = tg / L.ntiles_n;
+                TfTile T{};
+                if (GM) T = tiles[tg];
+                const int nkb = GM ? T.nkb : nkb_conv;
                 for (int kb = 0; kb < nkb; kb++, li++) {
                     const int as = li % L.na;
                     for (int h = 0; h < 2; h++) {
                         mbar_wait(smem_u32(&a_empty[h * TF_NA_MAX + as]), (uint32_t)(((li / L.na) & 1) ^ 1));
                         mbar_expect_tx(smem_u32(&raw_full[h * TF_NA_MAX + as]), a_img);
                         tma_load_2d(smem_u32(A0 + (size_t)((h * L.na + as) * 2) * a_img), &tm_x,
-                                    smem_u32(&raw_full[h * TF_NA_MAX + as]), kb * 32, (mp * 2 + h) * 128 + a.min_off);
+                                    smem_u32(&raw_full[h * TF_NA_MAX + as]), (GM ? T.a_col0 : 0) + kb * 32,
+                                    GM ? T.a_row0[h] : (mp * 2 + h) * 128 + a.min_off);
                     }
                 }
             }
@@ -204,33 +238,44 @@ __global__ void __launch_bounds__(TF_THREADS, 1) conv_tf_kernel(const ConvArgs a
         // ===================== converters: hi = v with 13 low mantissa bits cleared (in place), lo = tf32_rn(v - hi) ====
         const int ct = tid - TF_WARP_CONV0 * 32;
         const int nchunk = L.win * 8;                  // 16-byte chunks per image
-        const float slope = a.in_slope;
-        int li = 0;
+        const float slope = GM ? 1.f : a.in_slope;
+        auto split_image = [&](uint32_t hi_img, uint32_t lo_img, int n16) {
+            for (int idx = ct; idx < n16; idx += TF_NCONV) {
+                float4 v = lds128(hi_img + (uint32_t)idx * 16u);
+                if (slope != 1.f) {
+                    v.x = fmaxf(v.x, v.x * slope); v.y = fmaxf(v.y, v.y * slope);
+                    v.z = fmaxf(v.z, v.z * slope); v.w = fmaxf(v.w, v.w * slope);
+                }
+                uint4 hi, lo;
+                hi.x = __float_as_uint(v.x) & 0xffffe000u; hi.y = __float_as_uint(v.y) & 0xffffe000u;
+                hi.z = __float_as_uint(v.z) & 0xffffe000u; hi.w = __float_as_uint(v.w) & 0xffffe000u;
+                lo.x = __float_as_uint(tf32_rn(v.x - __uint_as_float(hi.x)));
+                lo.y = __float_as_uint(tf32_rn(v.y - __uint_as_float(hi.y)));
+                lo.z = __float_as_uint(tf32_rn(v.z - __uint_as_float(hi.z)));
+                lo.w = __float_as_uint(tf32_rn(v.w - __uint_as_float(hi.w)));
+                sts128u(hi_img + (uint32_t)idx * 16u, hi);
+                sts128u(lo_img + (uint32_t)idx * 16u, lo);
+            }
+            fence_async_smem();                        // generic-proxy stores -> visible to the tensor core
+        };
+        int li = 0, lw = 0;
         for (int tl = 0; tl < my_tiles; tl++) {
+            const int nkb = tile_nkb(tl);
             for (int kb = 0; kb < nkb; kb++, li++) {
                 const int as = li % L.na;
                 for (int h = 0; h < 2; h++) {
                     mbar_wait(smem_u32(&raw_full[h * TF_NA_MAX + as]), (uint32_t)((li / L.na) & 1));
                     const uint32_t hi_img = smem_u32(A0 + (size_t)((h * L.na + as) * 2) * a_img);
-                    const uint32_t lo_img = hi_img + a_img;
-                    for (int idx = ct; idx < nchunk; idx += TF_NCONV) {
-                        float4 v = lds128(hi_img + (uint32_t)idx * 16u);
-                        if (slope != 1.f) {
-                            v.x = fmaxf(v.x, v.x * slope); v.y = fmaxf(v.y, v.y * slope);
-                            v.z = fmaxf(v.z, v.z * slope); v.w = fmaxf(v.w, v.w * slope);
-                        }
-                        uint4 hi, lo;
-                        hi.x = __float_as_uint(v.x) & 0xffffe000u; hi.y = __float_as_uint(v.y) & 0xffffe000u;
-                        hi.z = __float_as_uint(v.z) & 0xffffe000u; hi.w = __float_as_uint(v.w) & 0xffffe000u;
-                        lo.x = __float_as_uint(tf32_rn(v.x - __uint_as_float(hi.x)));
-                        lo.y = __float_as_uint(tf32_rn(v.y - __uint_as_float(hi.y)));
-                        lo.z = __float_as_uint(tf32_rn(v.z - __uint_as_float(hi.z)));
-                        lo.w = __float_as_uint(tf32_rn(v.w - __uint_as_float(hi.w)));
-                        sts128u(hi_img + (uint32_t)idx * 16u, hi);
-                        sts128u(lo_img + (uint32_t)idx * 16u, lo);
-                    }
-                    fence_async_smem();                // generic-proxy stores -> visible to the tensor core
+                    split_image(hi_img, hi_img + a_img, nchunk);
                     mbar_arrive(smem_u32(&a_full[h * TF_NA_MAX + as]));
+                }
+                if (GM) {                              // the B operand of this K-block (same order as the issuers consume)
+                    const int ws = lw % L.nw;
+                    mbar_wait(smem_u32(&wraw_full[ws]), (uint32_t)((lw / L.nw) & 1));
+                    const uint32_t hi_img = smem_u32(W0 + (size_t)ws * 2 * w_img);
+                    split_image(hi_img, hi_img + w_img, L.nth * 8);
+                    mbar_arrive(smem_u32(&w_full[ws]));
+                    lw++;
                 }
             }
         }
@@ -239,12 +284,14 @@ __global__ void __launch_bounds__(TF_THREADS, 1) conv_tf_kernel(const ConvArgs a
         const int h = (warp - TF_WARP_EPI0) >> 2;
         const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
         const int row = quad * 32 + lane;
-        const int nchunks = (nkb + L.chunk_kb - 1) / L.chunk_kb;
         int lc = 0;
         for (int tl = 0; tl < my_tiles; tl++) {
             const int tg = (int)blockIdx.x + tl * (int)gridDim.x;
             const int q = ((tg / L.ntiles_n) * 2 + h) * 128 + row;
             const int n0 = (tg % L.ntiles_n) * L.nth;
+            TfTile T{};
+            if (GM) T = tiles[tg];
+            const int nchunks = ((GM ? T.nkb : nkb_conv) + L.chunk_kb - 1) / L.chunk_kb;
             float run[TF_NTH_MAX];
 #pragma unroll
             for (int j = 0; j < TF_NTH_MAX; j++) run[j] = 0.f;
@@ -265,8 +312,42 @@ __global__ void __launch_bounds__(TF_THREADS, 1) conv_tf_kernel(const ConvArgs a
                 tc_fence_before();
                 mbar_arrive(smem_u32(&acc_empty[h * 2 + st]));
             }
+            if (GM) {
+                // grouped GEMM: out = acc * scale (+ res), rows of this m-tile that belong to the utterance only
+                if (row >= T.rows_valid[h]) continue;
+                float* dst = a.y0 + T.out_off[h] + (size_t)row * a.ldy0;
+                const float* rsrc = a.res ? a.res + T.out_off[h] + (size_t)row * a.ldres : nullptr;
+#pragma unroll
+                for (int p = 0; p < TF_NTH_MAX / 8; p++) {
+                    if (p * 8 < L.nth) {
+                        float o[8], r[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) r[j] = 0.f;
+                        if (rsrc) ldg256(rsrc + p * 8, r);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) o[j] = fmaf(run[p * 8 + j], a.scale, r[j]);
+                        stg256(dst + p * 8, o);
+                    }
+                }
+                continue;
+            }
             if (q >= a.rows_q) continue;
             const bool valid = row_valid(a.map, q);
+            if (a.yt && n0 >= a.yt_col0) {
+                // transposed output tile (V of the fused q/k/v projection: the P.V contraction wants keys contiguous):
+                // yt[column][row]; the 32 lanes of a warp own 32 consecutive rows, so every store instruction writes one
+                // 128-byte line
+                float* dst = a.yt + (size_t)(n0 - a.yt_col0) * a.ldyt + q;
+#pragma unroll
+                for (int j = 0; j < TF_NTH_MAX; j++) {
+                    if (j < L.nth) {
+                        float o = run[j] + (a.bias ? a.bias[n0 + j] : 0.f);
+                        if (a.act == ACT_RELU) o = fmaxf(o, 0.f);
+                        dst[(size_t)j * a.ldyt] = valid ? o * a.scale : 0.f;
+                    }
+                }
+                continue;
+            }
             if (a.acc0 && !valid) continue;            // accumulated buffers keep their zeros in gap rows
             const size_t orow = (size_t)q + a.orow_add;
 #pragma unroll
@@ -341,7 +422,7 @@ bool plan(const ConvArgs& a, TfLaunch& L, size_t& smem) {
     // kind::tf32 instruction descriptor: D fp32 (1<<4), A = B = TF32 (2<<7, 2<<10), K-major both, N>>3, M>>4
     L.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(L.nth >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const size_t a_img = (size_t)L.win * 128, w_stage = (size_t)L.nth * 256;
-    const size_t bar_bytes = (2 * TF_NW_MAX + 6 * TF_NA_MAX + 8) * 8 + 16;
+    const size_t bar_bytes = (3 * TF_NW_MAX + 6 * TF_NA_MAX + 8) * 8 + 16;
     const size_t budget = 225 * 1024 - 2048;
     L.na = 2; L.nw = 2;
     auto total = [&]() { return (size_t)2 * L.na * 2 * a_img + (size_t)L.nw * w_stage + bar_bytes; };
@@ -376,7 +457,10 @@ bool conv_tf_supported(const ConvArgs& a) {
 
 void launch_conv_tf(const ConvArgs& a, cudaStream_t st) {
     static PerDeviceOnce once;
-    once.run([] { cudaFuncSetAttribute(conv_tf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+    once.run([] {
+        cudaFuncSetAttribute(conv_tf_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(conv_tf_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
     TfLaunch L; size_t smem;
     CUtensorMap tmx;
     if (!plan(a, L, smem) ||
@@ -386,9 +470,48 @@ void launch_conv_tf(const ConvArgs& a, cudaStream_t st) {
     }
     const int tiles = L.ntiles_mp * L.ntiles_n;
     const int grid = tiles < tf_num_sms() ? tiles : tf_num_sms();
-    conv_tf_kernel<<<grid, TF_THREADS, smem, st>>>(a, L, tmx);
+    conv_tf_kernel<0><<<grid, TfCfg<0>::THREADS, smem, st>>>(a, L, tmx, tmx, nullptr);
     g_launch_count++;
     check_launch("conv_tf");
+}
+
+bool gemm_tf_supported(const TfGemm& g) {
+    if (!tensor_map_encoder()) return false;
+    if (g.nth != 96 && g.nth != 64 && g.nth != 32) return false;
+    auto al = [](const void* p, int ld, int a) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0 && (ld & 3) == 0); };
+    return al(g.a, g.lda, 16) && al(g.b, g.ldb, 16) && al(g.y, g.ldy, 32) && (g.ldy & 7) == 0 && al(g.res, g.ldy, 32);
+}
+
+void launch_gemm_tf(const TfGemm& g, cudaStream_t st) {
+    static PerDeviceOnce once;
+    once.run([] {
+        cudaFuncSetAttribute(conv_tf_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(conv_tf_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
+    if (g.ntiles <= 0) return;
+    ConvArgs a{};
+    a.in_slope = 1.f; a.ntaps = 1; a.cin = 32; a.cout = g.nth;
+    a.y0 = g.y; a.ldy0 = g.ldy; a.res = g.res; a.ldres = g.ldy; a.scale = g.scale; a.split = g.nth; a.orow_mul = 1;
+    TfLaunch L{};
+    L.nth = g.nth; L.win = 128; L.ntiles_mp = g.ntiles; L.ntiles_n = 1; L.chunk_kb = 2;
+    L.tmem_cols = 32;
+    while (L.tmem_cols < 4 * L.nth) L.tmem_cols <<= 1;
+    L.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(L.nth >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const size_t a_img = 128 * 128, w_stage = (size_t)L.nth * 256;
+    const size_t bar_bytes = (3 * TF_NW_MAX + 6 * TF_NA_MAX + 8) * 8 + 16;
+    const size_t budget = 225 * 1024 - 2048;
+    L.na = 2; L.nw = 2;
+    auto total = [&]() { return (size_t)2 * L.na * 2 * a_img + (size_t)L.nw * w_stage + bar_bytes; };
+    while (L.nw < 4) { L.nw++; if (total() > budget) { L.nw--; break; } }
+    while (L.na < TF_NA_MAX) { L.na++; if (total() > budget) { L.na--; break; } }
+    CUtensorMap tma, tmb;
+    if (!tensor_map_2d(&tma, g.a, (unsigned long long)g.a_cols, (unsigned long long)g.a_rows, (unsigned long long)g.lda, 32, 128, true) ||
+        !tensor_map_2d(&tmb, g.b, (unsigned long long)g.b_cols, (unsigned long long)g.b_rows, (unsigned long long)g.ldb, 32, (unsigned)g.nth, true))
+        throw_launch_error("gemm_tf: tensor map encoding failed");
+    const int grid = g.ntiles < tf_num_sms() ? g.ntiles : tf_num_sms();
+    conv_tf_kernel<1><<<grid, TfCfg<1>::THREADS, total() + 2048, st>>>(a, L, tma, tmb, g.tiles);
+    g_launch_count++;
+    check_launch("gemm_tf");
 }
 
 // Host-side weight image builder: [n-tile][K-block][tap] stages; a stage = hi image (nth rows x 128 B) followed by the

@@ -7,8 +7,11 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 namespace sb200 {
+
+void throw_launch_error(const char* what) { throw Error(19, std::string("internal: ") + what); }
 
 void check_launch(const char* what) {
     const cudaError_t e = cudaGetLastError();
@@ -114,6 +117,43 @@ Job* create_job(Voice* v, const long long* ids, const size_t* offs, size_t B, co
         cur += round_up(n + HX, GX);
     }
     j->RX = round_up(cur, 256);
+    {
+        // Tile tables of the two attention GEMMs (conv_tf.cu, grouped mode).  S[head][row][key] = Q.K^T / sqrt(D):
+        // A = Q rows, B = K rows of the fused q/k/v activation [RX][3H]; O = P.V: A = P rows of S viewed as
+        // [heads*RX][Tp], B = V^T [H][RX] (the q/k/v projection stores V transposed).
+        const int H = v->a.hidden, heads = v->a.heads, D = H / heads;
+        j->att_tp = round_up(std::max(j->max_tx, 1), 96);
+        for (size_t b = 0; b < B; b++) {
+            const int off = j->xsegs[b].off, T = j->xsegs[b].len;
+            const int nmp = (T + 255) / 256, nnt = (T + 95) / 96;
+            for (int h = 0; h < heads; h++)
+                for (int mp = 0; mp < nmp; mp++) {
+                    TfTile t{};
+                    for (int m = 0; m < 2; m++) {
+                        const int r0 = (mp * 2 + m) * 128;
+                        t.rows_valid[m] = std::max(0, std::min(128, T - r0));
+                    }
+                    // Q.K^T: one tile per 96-key block
+                    for (int nt = 0; nt < nnt; nt++) {
+                        TfTile s = t;
+                        for (int m = 0; m < 2; m++) {
+                            s.a_row0[m] = off + (mp * 2 + m) * 128;
+                            s.out_off[m] = ((long long)h * j->RX + s.a_row0[m]) * j->att_tp + (long long)nt * 96;
+                        }
+                        s.a_col0 = h * D; s.b_row0 = off + nt * 96; s.b_col0 = H + h * D; s.nkb = D / 32;
+                        j->tiles_s.push_back(s);
+                    }
+                    // P.V: K runs over the utterance's keys in blocks of 32 (the softmax zero-fills up to the block end)
+                    TfTile o = t;
+                    for (int m = 0; m < 2; m++) {
+                        o.a_row0[m] = h * j->RX + off + (mp * 2 + m) * 128;
+                        o.out_off[m] = (long long)(off + (mp * 2 + m) * 128) * H + (long long)h * D;
+                    }
+                    o.a_col0 = 0; o.b_row0 = h * D; o.b_col0 = off; o.nkb = (T + 31) / 32;
+                    j->tiles_o.push_back(o);
+                }
+        }
+    }
     if (attention_smem_bytes(j->max_tx, v->a.hidden / v->a.heads) > 220 * 1024)
         throw Error(19, "Failed to run model inference. Error: sentence too long for one pass (" + std::to_string(j->max_tx) + " ids)");
     j->noise_call = ++v->call_counter;
@@ -149,6 +189,7 @@ struct Runner {
         int orow_mul = 1, orow_add = 0;
         bool tc_ok = false;
         bool tf_ok = false;    // duration-critical layer: tcgen05 3xTF32 with chunk-flushed accumulation (conv_tf.cu)
+        float* yt = nullptr; int yt_col0 = 0, ldyt = 0;     // conv_tf only: column tiles >= yt_col0 stored transposed
     };
     void conv(const ConvW& w, const float* x, int ldx, const Level& lin, const Opt& o) {
         ConvArgs p{};
@@ -160,6 +201,9 @@ struct Runner {
         p.act = o.act; p.scale = o.scale; p.res = o.res; p.ldres = o.ldres;
         p.y0 = o.y0; p.ldy0 = o.ldy0; p.acc0 = o.acc0; p.split = o.split < 0 ? w.cout : o.split;
         p.y1 = o.y1; p.ldy1 = o.ldy1; p.acc1 = o.acc1;
+        p.yt = o.yt; p.yt_col0 = o.yt_col0; p.ldyt = o.ldyt;
+        if (o.yt && !(v.backend == 1 && o.tf_ok && conv_tf_supported(p)))
+            throw Error(19, "internal: a transposed conv output needs the conv_tf kernel");
         // backend 1 (default): tcgen05 everywhere; 2: tcgen05 flow / decoder, fp32 CUDA cores for the text encoder and
         // the duration predictor (the round-1 configuration, kept for A/B runs); 0: fp32 CUDA cores everywhere
         if (v.backend == 1 && o.tf_ok && conv_tf_supported(p)) launch_conv_tf(p, st);
@@ -345,39 +389,62 @@ void Job::run(float* d_out, size_t d_out_cap) {
     if (!C.ev_begin) { SB_CUDA(cudaEventCreate(&C.ev_begin)); SB_CUDA(cudaEventCreate(&C.ev_end)); }
 
     // ---------------- phase 1 workspace ----------------
-    const size_t xfloats = (size_t)RX * (H * 6 + 3 * H + F + 2 * I + 32 + 2 + 2 + 1);
-    const size_t p1_bytes = xfloats * 4 + (size_t)RX * 16 + B * 64 + (1 << 20);
+    // tensor-core attention (two grouped GEMMs around a softmax): default backend, 96-wide heads, rows that fit the
+    // softmax kernel's registers; otherwise the fp32 CUDA-core attention kernel
+    const bool tc_att = V.backend == 1 && H / a.heads == 96 && max_tx <= 1280 && getenv("SB200_ATT_SIMT") == nullptr;
+    // xa xb qkv(3H) att d0 t1 t2 g = 10 H; ffn; stats; h29 32; zz 2 + eps_w 2; logw 1; + attention scratch (scores for
+    // every head, V^T, relative-value term)
+    const size_t xfloats = (size_t)RX * (H * 10 + F + 2 * I + 32 + 2 + 2 + 1) +
+                           (tc_att ? (size_t)a.heads * RX * att_tp + 2 * (size_t)RX * H : 0);
+    const size_t tile_bytes = (tiles_s.size() + tiles_o.size()) * sizeof(TfTile);
+    const size_t p1_bytes = xfloats * 4 + (size_t)RX * 20 + B * 64 + tile_bytes + (1 << 20) +
+                            (debug ? (size_t)RX * (4 * H + att_tp) * 4 + 4096 : 0);
     // The arena must also hold phase 2; sizes are only known after the durations come back, so phase 1
     // runs in the front of the arena and phase 2 re-plans behind it (growing = realloc would lose phase-1
     // results, so grow conservatively up front from the mean-duration estimate, then verify).
     const double est_frames = 4.0 * (double)ids.size() + 256.0 * B;
     size_t est_p2 = decoder_bytes(V, (int)std::min<double>(est_frames, 2.0e9 / 256), debug) + (size_t)(est_frames * I * 4 * 6);
     C.ensure_dev(p1_bytes + est_p2);
-    C.ensure_pin(std::max<size_t>((size_t)RX * 8 + B * 64 + (1 << 16), 1 << 20));
+    C.ensure_pin(std::max<size_t>((size_t)RX * 12 + B * 64 + tile_bytes + (1 << 16), 1 << 20));
     C.dev.used = 0; C.dev.dry = false;
     Runner R(*this);
 
     SB_CUDA(cudaEventRecord(C.ev_begin, st));
     // tables
     const int nxg = RX / GX;
-    std::vector<int> xend(nxg, 0);
+    std::vector<int> xend(nxg, 0), xseg_of(nxg, 0);
     int* ids_rows_h = reinterpret_cast<int*>(C.pin);
     for (int r = 0; r < RX; r++) ids_rows_h[r] = -1;
     for (size_t b = 0; b < B; b++) {
         const SegInfo& s = xsegs[b];
         for (int i = 0; i < s.len; i++) ids_rows_h[s.off + i] = (int)ids[offs[b] + i];
         const int g0 = s.off / GX, g1 = (b + 1 < B ? xsegs[b + 1].off : RX) / GX;
-        for (int g = g0; g < g1; g++) xend[g] = s.off + s.len;
+        for (int g = g0; g < g1; g++) { xend[g] = s.off + s.len; xseg_of[g] = (int)b; }
     }
     int* xend_h = ids_rows_h + RX;
     memcpy(xend_h, xend.data(), nxg * sizeof(int));
-    SegInfo* xsegs_h = reinterpret_cast<SegInfo*>(xend_h + nxg);
+    int* xseg_of_h = xend_h + nxg;
+    memcpy(xseg_of_h, xseg_of.data(), nxg * sizeof(int));
+    SegInfo* xsegs_h = reinterpret_cast<SegInfo*>(xseg_of_h + nxg);
     memcpy(xsegs_h, xsegs.data(), B * sizeof(SegInfo));
-    d_ids_rows = C.dev.get<int>(RX); d_xend = C.dev.get<int>(nxg); d_xsegs = C.dev.get<SegInfo>(B);
+    // result slot of the frame counts, then (8-byte aligned) the attention tile tables
+    const size_t ylen_off = ((size_t)RX * 4 + (size_t)nxg * 8 + B * sizeof(SegInfo) + 63) & ~(size_t)63;
+    const size_t tiles_off = (ylen_off + B * sizeof(int) + 63) & ~(size_t)63;
+    TfTile* tiles_h = reinterpret_cast<TfTile*>(C.pin + tiles_off);
+    d_ids_rows = C.dev.get<int>(RX); d_xend = C.dev.get<int>(nxg); d_xseg_of_gran = C.dev.get<int>(nxg); d_xsegs = C.dev.get<SegInfo>(B);
     d_cum = C.dev.get<int>(RX); d_ylen = C.dev.get<int>(B);
     h2d(d_ids_rows, ids_rows_h, (size_t)RX * 4, st);
     h2d(d_xend, xend_h, (size_t)nxg * 4, st);
+    h2d(d_xseg_of_gran, xseg_of_h, (size_t)nxg * 4, st);
     h2d(d_xsegs, xsegs_h, B * sizeof(SegInfo), st);
+    d_tiles_s = d_tiles_o = nullptr;
+    if (tc_att) {
+        memcpy(tiles_h, tiles_s.data(), tiles_s.size() * sizeof(TfTile));
+        memcpy(tiles_h + tiles_s.size(), tiles_o.data(), tiles_o.size() * sizeof(TfTile));
+        d_tiles_s = C.dev.get<TfTile>(tiles_s.size() + tiles_o.size());
+        d_tiles_o = d_tiles_s + tiles_s.size();
+        h2d(d_tiles_s, tiles_h, tile_bytes, st);
+    }
 
     Level LX; LX.map = {d_xend, GX, 1, RX}; LX.valid_rows = (long long)ids.size();
     float* xa = C.dev.get<float>((size_t)RX * H);
@@ -393,6 +460,23 @@ void Job::run(float* d_out, size_t d_out_cap) {
     float* h29 = C.dev.get<float>((size_t)RX * 32);
     float* zz = C.dev.get<float>((size_t)RX * 2);
     float* logw = C.dev.get<float>((size_t)RX);
+    float *att_s = nullptr, *att_vt = nullptr, *att_orel = nullptr;
+    TfGemm gs{}, go{};
+    bool tc_att_ok = tc_att;
+    if (tc_att) {
+        att_s = C.dev.get<float>((size_t)a.heads * RX * att_tp);
+        att_vt = C.dev.get<float>((size_t)H * RX);
+        att_orel = C.dev.get<float>((size_t)RX * H);
+        gs.a = qkv; gs.a_rows = RX; gs.a_cols = 3 * H; gs.lda = 3 * H;
+        gs.b = qkv; gs.b_rows = RX; gs.b_cols = 3 * H; gs.ldb = 3 * H;
+        gs.nth = 96; gs.y = att_s; gs.ldy = att_tp; gs.res = nullptr; gs.scale = 1.0f / sqrtf((float)(H / a.heads));
+        gs.tiles = d_tiles_s; gs.ntiles = (int)tiles_s.size();
+        go.a = att_s; go.a_rows = a.heads * RX; go.a_cols = att_tp; go.lda = att_tp;
+        go.b = att_vt; go.b_rows = H; go.b_cols = RX; go.ldb = RX;
+        go.nth = 96; go.y = att; go.ldy = H; go.res = att_orel; go.scale = 1.f;
+        go.tiles = d_tiles_o; go.ntiles = (int)tiles_o.size();
+        tc_att_ok = gemm_tf_supported(gs) && gemm_tf_supported(go);
+    }
     d_epsw = nullptr;
     if (cfg.noise_w != 0.f) {
         d_epsw = C.dev.get<float>((size_t)RX * 2);
@@ -408,16 +492,41 @@ void Job::run(float* d_out, size_t d_out_cap) {
     }
 
     // ---------------- text encoder ----------------
-    // (kept on the fp32 CUDA-core kernel: the duration predictor reads x, and ceil(duration) is a cliff --
-    //  3xTF32 moves logw by ~1e-4, fp32 by ~5e-6)
+    // Every contraction here reaches the duration predictor, and ceil(duration) is a cliff: the dense layers and the two
+    // attention contractions run on conv_tf.cu (tcgen05, error-compensated tf32, chunk-flushed accumulation: fp32-class
+    // accuracy); backend 0 / 2 keep them on the fp32 CUDA-core kernels.
     R.begin("enc");
     launch_embed(d_ids_rows, V.emb, sqrtf((float)H), xa, RX, H, st);
     R.count(0, 4.0 * LX.valid_rows * H);
     for (int l = 0; l < a.layers; l++) {
         const EncLayer& e = V.enc[l];
-        { Runner::Opt o; o.y0 = qkv; o.ldy0 = 3 * H; o.tf_ok = true; R.conv(e.qkv, xa, H, LX, o); }
-        launch_attention(qkv, 3 * H, e.relk, e.relv, a.window, att, H, H, a.heads, d_xsegs, (int)B, max_tx, st);
+        {
+            Runner::Opt o; o.y0 = qkv; o.ldy0 = 3 * H; o.tf_ok = true;
+            if (tc_att_ok) { o.yt = att_vt; o.yt_col0 = 2 * H; o.ldyt = RX; }       // V leaves transposed: [H][RX]
+            R.conv(e.qkv, xa, H, LX, o);
+        }
+        if (tc_att_ok) {
+            launch_gemm_tf(gs, st);
+            launch_attn_softmax(att_s, att_tp, qkv, 3 * H, e.relk, e.relv, a.window, att_orel, H, H, a.heads, RX, d_xsegs,
+                                d_xseg_of_gran, GX, max_tx, st);
+            launch_gemm_tf(go, st);
+            R.count(0, 0, 2);
+        } else {
+            launch_attention(qkv, 3 * H, e.relk, e.relv, a.window, att, H, H, a.heads, d_xsegs, (int)B, max_tx, st);
+        }
         { double f = 0; for (auto& s : xsegs) f += 4.0 * (double)s.len * s.len * H; R.count(f, 16.0 * LX.valid_rows * H); }
+        if (debug && l == 0) {      // first-layer attention operands / result (tools/debug_att.py)
+            float* qk = C.dev.get<float>((size_t)RX * 3 * H);
+            float* at = C.dev.get<float>((size_t)RX * H);
+            SB_CUDA(cudaMemcpyAsync(qk, qkv, (size_t)RX * 3 * H * 4, cudaMemcpyDeviceToDevice, st));
+            SB_CUDA(cudaMemcpyAsync(at, att, (size_t)RX * H * 4, cudaMemcpyDeviceToDevice, st));
+            dbg["qkv0"] = {qk, 3 * H}; dbg_level["qkv0"] = 0; dbg["att0"] = {at, H}; dbg_level["att0"] = 0;
+            if (tc_att_ok) {
+                float* sp = C.dev.get<float>((size_t)RX * att_tp);
+                SB_CUDA(cudaMemcpyAsync(sp, att_s, (size_t)RX * att_tp * 4, cudaMemcpyDeviceToDevice, st));
+                dbg["p0"] = {sp, att_tp}; dbg_level["p0"] = 0;     // head 0 probabilities
+            }
+        }
         { Runner::Opt o; o.y0 = xb; o.ldy0 = H; o.tf_ok = true; R.conv(e.o, att, H, LX, o); }
         launch_ln(xa, xb, nullptr, e.g1, e.b1, xa, H, 0, LX.map, st);
         R.count(0, 12.0 * LX.valid_rows * H);
@@ -449,7 +558,7 @@ void Job::run(float* d_out, size_t d_out_cap) {
     if (debug) { dbg["logw"] = {logw, 1}; dbg_level["logw"] = 0; }
 
     // ---------------- host learns the frame counts (the graph's data-dependent shape) ----------------
-    int* ylen_h = reinterpret_cast<int*>(C.pin + (size_t)RX * 4 + (size_t)nxg * 4 + B * sizeof(SegInfo) + 64);
+    int* ylen_h = reinterpret_cast<int*>(C.pin + ylen_off);
     SB_CUDA(cudaMemcpyAsync(ylen_h, d_ylen, B * sizeof(int), cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaStreamSynchronize(st));
     y_len.assign(ylen_h, ylen_h + B);
@@ -478,7 +587,7 @@ void Job::run(float* d_out, size_t d_out_cap) {
             SB_CUDA(cudaStreamSynchronize(st));
             const ptrdiff_t delta = C.dev.base - old.base;
             auto mv = [&](auto*& ptr) { if (ptr) ptr = reinterpret_cast<std::remove_reference_t<decltype(ptr)>>(reinterpret_cast<char*>(ptr) + delta); };
-            mv(d_ids_rows); mv(d_xend); mv(d_xsegs); mv(d_cum); mv(d_ylen); mv(d_epsw);
+            mv(d_ids_rows); mv(d_xend); mv(d_xsegs); mv(d_cum); mv(d_ylen); mv(d_epsw); mv(d_xseg_of_gran); mv(d_tiles_s); mv(d_tiles_o);
             mv(xa); mv(stats); mv(logw);
             for (auto& kv : dbg) kv.second.first = reinterpret_cast<float*>(reinterpret_cast<char*>(kv.second.first) + delta);
             SB_CUDA(cudaFree(old.base));

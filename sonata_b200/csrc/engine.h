@@ -170,6 +170,10 @@ struct Job {
     // device pointers (ctx arena)
     int *d_ids_rows = nullptr, *d_xend = nullptr, *d_cum = nullptr, *d_ylen = nullptr, *d_yend = nullptr, *d_ftile = nullptr;
     SegInfo* d_xsegs = nullptr; FrameSeg* d_fsegs = nullptr;
+    // tensor-core attention (conv_tf.cu grouped GEMMs): tile tables built with the X layout, same for every layer
+    std::vector<TfTile> tiles_s, tiles_o;      // Q.K^T tiles, P.V tiles
+    int att_tp = 0;                            // key columns of a score row (multiple of 96)
+    int* d_xseg_of_gran = nullptr; TfTile *d_tiles_s = nullptr, *d_tiles_o = nullptr;
     float *d_epsw = nullptr, *d_epsz = nullptr;
     float* d_wav = nullptr; bool wav_external = false;
     std::map<std::string, std::pair<float*, int>> dbg;   // name -> (device ptr, cols)

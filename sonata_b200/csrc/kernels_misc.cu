@@ -278,6 +278,88 @@ __global__ void __launch_bounds__(2 * D) attention_kernel(const float* __restric
     }
 }
 
+// ------------------------------------------------------------------ relative-position softmax (tensor-core attention)
+// Sits between the two grouped GEMMs of conv_tf.cu.  S[head][row][key] = (q.k)/sqrt(D) arrives from the first GEMM;
+// one warp per (row, head) adds the relative-key logits on the |j - i| <= window band, takes the softmax over the
+// utterance's keys IN PLACE, zero-fills the row up to the next multiple of 32 keys (the K extent of the second GEMM) and
+// writes the relative-value term  orel[row][head*D + c] = sum_d p[i][i+d] E_v[d+w][c],  which the second GEMM adds as
+// its residual.  The whole row lives in registers (NREG x 32 keys).  oracle: _mha()
+template <int D, int NREG>
+__global__ void __launch_bounds__(256) attn_softmax_kernel(float* __restrict__ S, int Tp, const float* __restrict__ qkv,
+                                                           int ldq, const float* __restrict__ relk,
+                                                           const float* __restrict__ relv, int window,
+                                                           float* __restrict__ orel, int ldo, int RX,
+                                                           const SegInfo* __restrict__ segs,
+                                                           const int* __restrict__ seg_of_gran, int gran) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * 8 + warp;
+    const int head = blockIdx.y;
+    if (q >= RX) return;
+    const SegInfo sg = segs[seg_of_gran[q / gran]];
+    const int i = q - sg.off, T = sg.len;
+    if (i < 0 || i >= T) return;                       // gap row
+    float* Sr = S + ((size_t)head * RX + q) * Tp;
+    const int nrel = 2 * window + 1;
+    constexpr int NV = D / 32;
+    const float qs = rsqrtf((float)D);
+    float qv[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) qv[k] = qkv[(size_t)q * ldq + head * D + lane + 32 * k] * qs;
+    float mine = 0.f;                                  // lane d keeps the logit of relative offset d - window
+    for (int d = 0; d < nrel; d++) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; k++) s = fmaf(qv[k], relk[d * D + lane + 32 * k], s);
+        s = warp_sum(s);
+        if (lane == d) mine = s;
+    }
+    if (lane < nrel) {
+        const int j = i + lane - window;
+        if (j >= 0 && j < T) Sr[j] += mine;
+    }
+    __syncwarp();
+    float s[NREG];
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < NREG; k++) {
+        const int j = lane + 32 * k;
+        s[k] = j < T ? Sr[j] : -INFINITY;
+        m = fmaxf(m, s[k]);
+    }
+    m = warp_max(m);
+    float l = 0.f;
+#pragma unroll
+    for (int k = 0; k < NREG; k++) {
+        const float e = (lane + 32 * k) < T ? expf(s[k] - m) : 0.f;
+        s[k] = e;
+        l += e;
+    }
+    l = warp_sum(l);
+    const float inv = 1.f / l;
+    const int Tz = (T + 31) & ~31;
+#pragma unroll
+    for (int k = 0; k < NREG; k++) {
+        const int j = lane + 32 * k;
+        if (j < Tz) Sr[j] = s[k] * inv;
+    }
+    __syncwarp();
+    float pb = 0.f;
+    if (lane < nrel) {
+        const int j = i + lane - window;
+        if (j >= 0 && j < T) pb = Sr[j];
+    }
+    float acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) acc[k] = 0.f;
+    for (int d = 0; d < nrel; d++) {
+        const float p = __shfl_sync(0xffffffffu, pb, d);
+#pragma unroll
+        for (int k = 0; k < NV; k++) acc[k] = fmaf(p, relv[d * D + lane + 32 * k], acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < NV; k++) orel[(size_t)q * ldo + head * D + lane + 32 * k] = acc[k];
+}
+
 // ------------------------------------------------------------------ duration-predictor flow pieces
 // oracle: _conv_flow_reverse()  h = pre(z0) + g
 __global__ void flow_pre_kernel(const float* __restrict__ z, int zcol, const float* __restrict__ w,
@@ -582,7 +664,7 @@ void launch_ln(const float* x, const float* res1, const float* res2, const float
         case 96: ln_kernel<3><<<grid, 256, 0, st>>>(x, res1, res2, gamma, beta, out, act, map); break;
         case 192: ln_kernel<6><<<grid, 256, 0, st>>>(x, res1, res2, gamma, beta, out, act, map); break;
         case 256: ln_kernel<8><<<grid, 256, 0, st>>>(x, res1, res2, gamma, beta, out, act, map); break;
-        default: break;
+        default: throw_launch_error("LayerNorm: unsupported channel count (96 / 192 / 256)");
     }
     g_launch_count++;
 }
@@ -594,7 +676,7 @@ void launch_dw_ln_gelu(const float* x, const float* wdw, const float* bdw, int k
         case 96: dw_ln_gelu_kernel<3><<<grid, 256, 0, st>>>(x, wdw, bdw, k, dil, gamma, beta, out, map); break;
         case 192: dw_ln_gelu_kernel<6><<<grid, 256, 0, st>>>(x, wdw, bdw, k, dil, gamma, beta, out, map); break;
         case 256: dw_ln_gelu_kernel<8><<<grid, 256, 0, st>>>(x, wdw, bdw, k, dil, gamma, beta, out, map); break;
-        default: break;
+        default: throw_launch_error("DDSConv: unsupported channel count (96 / 192 / 256)");
     }
     g_launch_count++;
 }
@@ -618,7 +700,20 @@ void launch_attention(const float* qkv, int ldq, const float* relk, const float*
     } else if (D == 48) {
         set_smem(attention_kernel<48>, smem);
         attention_kernel<48><<<grid, 96, smem, st>>>(qkv, ldq, relk, relv, window, out, ldo, H, segs, tpad);
-    }
+    } else throw_launch_error("attention: unsupported head size (96 / 48)");
+    g_launch_count++;
+}
+
+void launch_attn_softmax(float* S, int Tp, const float* qkv, int ldq, const float* relk, const float* relv, int window,
+                         float* orel, int ldo, int H, int heads, int RX, const SegInfo* segs, const int* seg_of_gran,
+                         int gran, int max_len, cudaStream_t st) {
+    const int D = H / heads;
+    dim3 grid((RX + 7) / 8, heads);
+    if (D != 96 || max_len > 1280 || 2 * window + 1 > 32) throw_launch_error("attn_softmax: unsupported head size / length");
+    if (max_len <= 640)
+        attn_softmax_kernel<96, 20><<<grid, 256, 0, st>>>(S, Tp, qkv, ldq, relk, relv, window, orel, ldo, RX, segs, seg_of_gran, gran);
+    else
+        attn_softmax_kernel<96, 40><<<grid, 256, 0, st>>>(S, Tp, qkv, ldq, relk, relv, window, orel, ldo, RX, segs, seg_of_gran, gran);
     g_launch_count++;
 }
 
@@ -662,7 +757,7 @@ void launch_conv_post(const float* x, int C, const float* w, float* wav, const F
         case 16: set_smem(conv_post_kernel<16>, smem); conv_post_kernel<16><<<grid, 256, smem, st>>>(x, w, wav, fsegs, ftile_seg, U, map); break;
         case 32: set_smem(conv_post_kernel<32>, smem); conv_post_kernel<32><<<grid, 256, smem, st>>>(x, w, wav, fsegs, ftile_seg, U, map); break;
         case 64: set_smem(conv_post_kernel<64>, smem); conv_post_kernel<64><<<grid, 256, smem, st>>>(x, w, wav, fsegs, ftile_seg, U, map); break;
-        default: break;
+        default: throw_launch_error("conv_post: unsupported channel count (16 / 32 / 64)");
     }
     g_launch_count++;
 }
