@@ -238,7 +238,7 @@ int32_t sb200_job_fetch_i16(sb200_job* job, int16_t** outs, size_t* lens, sb200_
         short* d_i16 = nullptr; unsigned* d_max = nullptr;
         SB_CUDA(cudaMallocAsync(&d_i16, (size_t)j.total_samples * 2 + 16, j.ctx->stream));
         SB_CUDA(cudaMallocAsync(&d_max, sizeof(unsigned) * j.B, j.ctx->stream));
-        launch_i16(j.d_wav, j.d_fsegs, (int)j.B, hop, mx, d_max, d_i16, j.ctx->stream);
+        launch_i16(j.d_wav, j.d_fsegs, (int)j.B, hop, mx, d_max, d_i16, PcmPost{}, j.ctx->stream);
         PinnedBlock* blk = pin_acquire((size_t)j.total_samples * 2 + 16);
         cudaError_t e = cudaMemcpyAsync(blk->base, d_i16, (size_t)j.total_samples * 2, cudaMemcpyDeviceToHost, j.ctx->stream);
         cudaFreeAsync(d_i16, j.ctx->stream);
@@ -275,7 +275,7 @@ int32_t sb200_job_copy_out(sb200_job* job, void* dst, size_t cap, int32_t format
             short* d_i16 = nullptr; unsigned* d_max = nullptr;
             SB_CUDA(cudaMallocAsync(&d_i16, n * 2 + 16, st));
             SB_CUDA(cudaMallocAsync(&d_max, sizeof(unsigned) * j.B, st));
-            launch_i16(j.d_wav, j.d_fsegs, (int)j.B, hop, mx, d_max, d_i16, st);
+            launch_i16(j.d_wav, j.d_fsegs, (int)j.B, hop, mx, d_max, d_i16, PcmPost{}, st);
             cudaError_t e = cudaMemcpyAsync(dst, d_i16, bytes, cudaMemcpyDeviceToHost, st);
             cudaFreeAsync(d_i16, st);
             cudaFreeAsync(d_max, st);

@@ -152,8 +152,11 @@ void launch_expand(const float* stats, int ldst, int I, const int* cum, const fl
 void launch_conv_post(const float* x, int C, const float* w /*[7][C]*/, float* wav, const FrameSeg* fsegs,
                       const int* ftile_seg, int U, RowMap map, cudaStream_t st);
 // per-utterance peak-normalised f32 -> i16 (audio-ops `to_i16_vec`), out indexed like wav
+// what the reference applies to a chunk before the 16-bit conversion (see kernels_misc.cu): overlap trim (samples),
+// crossfade table of fade_n <= 48 entries, linear gain.  Default = plain to_i16_vec.
+struct PcmPost { float gain = 1.f; int fade_n = 0; long long trim_lo = 0, trim_hi = 0; float tab[48] = {0}; };
 void launch_i16(const float* wav, const FrameSeg* fsegs, int nseg, int hop, long long max_samples, unsigned* maxbits,
-                short* out, cudaStream_t st);
+                short* out, const PcmPost& post, cudaStream_t st);
 void launch_randn(float* out, long long n, unsigned long long seed, unsigned long long stream_id, cudaStream_t st);
 void launch_scale_copy2(const float* eps, float s, float* z, RowMap map, cudaStream_t st);   // z[r][0..1] = eps*s
 void launch_fill_zero(float* p, long long n, cudaStream_t st);

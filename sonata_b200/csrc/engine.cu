@@ -685,16 +685,18 @@ Latent* encode_latent(Voice* v, const long long* ids, size_t n) {
     return L.release();
 }
 
-void decode_latent_chunk(Voice* v, const Latent* z, long long lo, long long hi, std::vector<float>& out, float* ms) {
+namespace {
+// decoder on z[lo:hi) with the result left on the device (job-owned arena): shared by the f32 and the PCM entry points
+float* decode_chunk_device(Voice* v, const Latent* z, long long lo, long long hi, Job& j, size_t extra_bytes) {
     if (lo < 0 || hi > z->frames || lo >= hi) throw Error(19, "Invalid model audio output");
     const Arch& a = v->a;
-    Job j; j.v = v; j.B = 1; j.ctx = v->acquire();
+    j.v = v; j.B = 1; j.ctx = v->acquire();
     Context& C = *j.ctx;
     SB_CUDA(cudaSetDevice(v->device));
     const int n = (int)(hi - lo);
     const int RY = round_up(n + HY, GY);
-    C.ensure_dev(decoder_bytes(*v, RY, false) + (size_t)RY * a.inter * 4 + (size_t)n * a.hop() * 4 + (4 << 20));
-    C.ensure_pin(1 << 20);
+    C.ensure_dev(decoder_bytes(*v, RY, false) + (size_t)RY * a.inter * 4 + (size_t)n * a.hop() * 4 + extra_bytes + (4 << 20));
+    C.ensure_pin(std::max<size_t>(1 << 20, (size_t)n * a.hop() * 4 + 4096));
     C.dev.used = 0; C.events_used = 0;
     if (!C.ev_begin) { SB_CUDA(cudaEventCreate(&C.ev_begin)); SB_CUDA(cudaEventCreate(&C.ev_end)); }
     cudaStream_t st = C.stream;
@@ -707,11 +709,83 @@ void decode_latent_chunk(Voice* v, const Latent* z, long long lo, long long hi, 
     float* d_wav = C.dev.get<float>((size_t)j.total_samples + 4);
     run_decoder(R, LY, s, d_wav, j.d_fsegs, j.d_ftile, j.d_yend);
     SB_CUDA(cudaEventRecord(C.ev_end, st));
-    out.resize((size_t)j.total_samples);
-    SB_CUDA(cudaMemcpyAsync(out.data(), d_wav, out.size() * 4, cudaMemcpyDeviceToHost, st));
+    return d_wav;
+}
+}  // namespace
+
+void decode_latent_chunk(Voice* v, const Latent* z, long long lo, long long hi, std::vector<float>& out, float* ms) {
+    Job j;
+    float* d_wav = decode_chunk_device(v, z, lo, hi, j, 0);
+    Context& C = *j.ctx;
+    cudaStream_t st = C.stream;
+    // through the context's page-locked staging buffer: a DMA copy instead of a pageable one
+    const size_t bytes = (size_t)j.total_samples * 4;
+    SB_CUDA(cudaMemcpyAsync(C.pin, d_wav, bytes, cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaStreamSynchronize(st));
     SB_CUDA(cudaGetLastError());
+    out.resize((size_t)j.total_samples);
+    memcpy(out.data(), C.pin, bytes);
     if (ms) cudaEventElapsedTime(ms, C.ev_begin, C.ev_end);
+}
+
+// crossfade table of AudioSamples::crossfade (audio/ops/src/samples.rs:144-157) for a buffer of `len` samples
+static void fill_fade(PcmPost& p, int fade, long long len) {
+    const long long n = std::min<long long>(fade, len / 2);
+    p.fade_n = (int)std::min<long long>(n, 48);
+    const float att = (float)(p.fade_n - 1);
+    for (int i = 0; i < p.fade_n; i++) p.tab[i] = sinf(((float)i / att) * 3.14159265358979f / 2.0f);
+}
+
+void decode_latent_chunk_pcm(Voice* v, const Latent* z, long long lo, long long hi, long long trim_lo_frames,
+                             long long trim_hi_frames, int fade, float gain, std::vector<int16_t>& out, float* ms) {
+    Job j;
+    const int hop = v->a.hop();
+    const size_t total = (size_t)(hi - lo) * hop;
+    float* d_wav = decode_chunk_device(v, z, lo, hi, j, total * 2 + 4096);
+    Context& C = *j.ctx;
+    cudaStream_t st = C.stream;
+    PcmPost post;
+    post.gain = gain; post.trim_lo = trim_lo_frames * hop; post.trim_hi = trim_hi_frames * hop;
+    const long long m = (long long)total - post.trim_lo - post.trim_hi;
+    if (m <= 0) throw Error(19, "Invalid model audio output");
+    if (fade > 0) fill_fade(post, fade, m);
+    short* d_i16 = C.dev.get<short>(total + 8);
+    unsigned* d_max = C.dev.get<unsigned>(4);
+    launch_i16(d_wav, j.d_fsegs, 1, hop, (long long)total, d_max, d_i16, post, st);
+    SB_CUDA(cudaMemcpyAsync(C.pin, d_i16, (size_t)m * 2, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    SB_CUDA(cudaGetLastError());
+    out.resize((size_t)m);
+    memcpy(out.data(), C.pin, (size_t)m * 2);
+    if (ms) cudaEventElapsedTime(ms, C.ev_begin, C.ev_end);
+}
+
+// Peak-normalised 16-bit PCM of every utterance of a finished job (to_i16_vec after the linear gain), converted on the
+// device and copied through the context's page-locked staging buffer.
+void job_pcm16(Job& j, float gain, std::vector<std::vector<int16_t>>& out) {
+    if (!j.ran || j.encode_only) throw Error(19, "job has not produced audio");
+    Voice& v = *j.v; Context& C = *j.ctx;
+    SB_CUDA(cudaSetDevice(v.device));
+    cudaStream_t st = C.stream;
+    const int hop = v.a.hop();
+    const size_t n = (size_t)j.total_samples;
+    long long mx = 0;
+    for (size_t b = 0; b < j.B; b++) mx = std::max<long long>(mx, (long long)j.y_len[b] * hop);
+    short* d_i16 = nullptr; unsigned* d_max = nullptr;
+    SB_CUDA(cudaMallocAsync(&d_i16, n * 2 + 16, st));
+    SB_CUDA(cudaMallocAsync(&d_max, sizeof(unsigned) * j.B, st));
+    PcmPost post; post.gain = gain;
+    launch_i16(j.d_wav, j.d_fsegs, (int)j.B, hop, mx, d_max, d_i16, post, st);
+    C.ensure_pin(n * 2 + 4096);                    // the tables staged there were consumed by the pass
+    cudaError_t e = cudaMemcpyAsync(C.pin, d_i16, n * 2, cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(d_i16, st);
+    cudaFreeAsync(d_max, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) throw Error(19, std::string("CUDA error: ") + cudaGetErrorString(e));
+    out.resize(j.B);
+    const int16_t* h = reinterpret_cast<const int16_t*>(C.pin);
+    for (size_t b = 0; b < j.B; b++)
+        out[b].assign(h + j.fsegs[b].out_off, h + j.fsegs[b].out_off + (size_t)j.y_len[b] * hop);
 }
 
 }  // namespace sb200

@@ -197,5 +197,10 @@ struct Latent {
 };
 Latent* encode_latent(Voice* v, const long long* ids, size_t n);
 void decode_latent_chunk(Voice* v, const Latent* z, long long lo, long long hi, std::vector<float>& out, float* ms);
+// the same chunk as peak-normalised i16 PCM with the reference's post-path done on the DEVICE: drop trim_lo / trim_hi
+// overlap frames, crossfade(fade) (samples.rs:144-157), linear gain, to_i16_vec (samples.rs:51-75)
+void decode_latent_chunk_pcm(Voice* v, const Latent* z, long long lo, long long hi, long long trim_lo_frames,
+                             long long trim_hi_frames, int fade, float gain, std::vector<int16_t>& out, float* ms);
+void job_pcm16(Job& j, float gain, std::vector<std::vector<int16_t>>& out);
 
 }  // namespace sb200

@@ -574,30 +574,42 @@ __global__ void __launch_bounds__(256) conv_post_kernel(const float* __restrict_
 // ------------------------------------------------------------------ f32 -> i16 with per-utterance peak normalisation
 // crates/audio/ops/src/samples.rs:51-75 (`to_i16_vec`): scale = 32767 / max(|x|_max, f32::EPSILON);
 // y = trunc(clamp(x * scale, -32768, 32767)).  Bit-exact with the host version (same fp32 operations in the same
-// order); halves the device->host bytes of a synthesis result.
+// order); halves the device->host bytes of a synthesis result.  `PcmPost` folds in what the reference does to a
+// chunk before that conversion: trimming the overlap frames of a streamed chunk (piper/src/lib.rs:811-826),
+// crossfade(42) (samples.rs:144-157; the sine table is computed by the host so both sides use the same floats) and
+// the linear volume gain of AudioOutputConfig (synth/src/lib.rs:84-86).
+__device__ __forceinline__ float pcm_value(const float* __restrict__ x, long long i, long long m, const PcmPost& p) {
+    float v = x[i];
+    if (p.fade_n > 0) {
+        if (i < p.fade_n) v = __fmul_rn(v, p.tab[i]);
+        else if (i >= m - p.fade_n) v = __fmul_rn(v, p.tab[m - 1 - i]);
+    }
+    return p.gain == 1.f ? v : __fmul_rn(v, p.gain);
+}
+
 __global__ void i16_absmax_kernel(const float* __restrict__ wav, const FrameSeg* __restrict__ fsegs, int hop,
-                                  unsigned* __restrict__ maxbits) {
+                                  unsigned* __restrict__ maxbits, const PcmPost post) {
     const FrameSeg fs = fsegs[blockIdx.y];
-    const long long n = (long long)fs.len * hop;
-    const float* x = wav + fs.out_off;
+    const long long n = (long long)fs.len * hop - post.trim_lo - post.trim_hi;
+    const float* x = wav + fs.out_off + post.trim_lo;
     float m = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        m = fmaxf(m, fabsf(x[i]));
+        m = fmaxf(m, fabsf(pcm_value(x, i, n, post)));
     m = warp_max(m);
     if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(maxbits + blockIdx.y, __float_as_uint(m));   // non-negative floats
                                                                                                   // order like their bits
 }
 
 __global__ void i16_convert_kernel(const float* __restrict__ wav, const FrameSeg* __restrict__ fsegs, int hop,
-                                   const unsigned* __restrict__ maxbits, short* __restrict__ out) {
+                                   const unsigned* __restrict__ maxbits, short* __restrict__ out, const PcmPost post) {
     const FrameSeg fs = fsegs[blockIdx.y];
-    const long long n = (long long)fs.len * hop;
-    const float* x = wav + fs.out_off;
+    const long long n = (long long)fs.len * hop - post.trim_lo - post.trim_hi;
+    const float* x = wav + fs.out_off + post.trim_lo;
     short* y = out + fs.out_off;
     const float amax = fmaxf(__uint_as_float(maxbits[blockIdx.y]), 1.1920928955078125e-07f);
     const float scale = __fdiv_rn(32767.0f, amax);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const float v = fminf(fmaxf(__fmul_rn(x[i], scale), -32768.0f), 32767.0f);
+        const float v = fminf(fmaxf(__fmul_rn(pcm_value(x, i, n, post), scale), -32768.0f), 32767.0f);
         y[i] = (short)(int)v;                      // truncating cast
     }
 }
@@ -763,15 +775,15 @@ void launch_conv_post(const float* x, int C, const float* w, float* wav, const F
 }
 
 void launch_i16(const float* wav, const FrameSeg* fsegs, int nseg, int hop, long long max_samples, unsigned* maxbits,
-                short* out, cudaStream_t st) {
+                short* out, const PcmPost& post, cudaStream_t st) {
     if (nseg <= 0) return;
     cudaMemsetAsync(maxbits, 0, sizeof(unsigned) * nseg, st);
     int bx = (int)((max_samples + 256 * 8 - 1) / (256 * 8));
     if (bx < 1) bx = 1;
     if (bx > 1024) bx = 1024;
     dim3 grid(bx, nseg);
-    i16_absmax_kernel<<<grid, 256, 0, st>>>(wav, fsegs, hop, maxbits);
-    i16_convert_kernel<<<grid, 256, 0, st>>>(wav, fsegs, hop, maxbits, out);
+    i16_absmax_kernel<<<grid, 256, 0, st>>>(wav, fsegs, hop, maxbits, post);
+    i16_convert_kernel<<<grid, 256, 0, st>>>(wav, fsegs, hop, maxbits, out, post);
     g_launch_count += 2;
 }
 

@@ -12,9 +12,15 @@
 // Event payloads are i16 LE PCM, peak-normalised per chunk exactly like AudioSamples::as_wave_bytes
 // (audio/ops/src/samples.rs:51-78); realtime mode uses the reference chunk schedule (72, 3) with
 // crossfade(42) (piper/src/lib.rs:765-913) and the chunk-size growth rule of synth/src/lib.rs:348-356.
+// The whole post-path -- overlap trim, crossfade, volume gain, peak normalisation, 16-bit conversion -- runs on the
+// DEVICE (kernels_misc.cu i16 kernels, bit-identical to the host arithmetic of the reference): a callback receives
+// bytes that crossed PCIe once, as i16, through page-locked staging.
+// The voice is reference-counted like the reference's Arc (capi/src/lib.rs:314,375): a non-blocking speak keeps it
+// alive after libsonataUnloadSonataVoice.
 #include "engine.h"
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include <thread>
 
 using namespace sb200;
@@ -22,7 +28,7 @@ using namespace sb200;
 extern "C" {
 
 // ---- ABI types: same field order / widths as capi/libsonata.h:32-76 ----
-typedef struct SonataVoice { Voice* v; } SonataVoice;
+typedef struct SonataVoice { std::shared_ptr<Voice> v; } SonataVoice;
 typedef struct PiperSynthConfig { uint32_t speaker; float length_scale; float noise_scale; float noise_w; } PiperSynthConfig;
 typedef struct ExternError { int32_t code; char* message; } ExternError;
 typedef struct SynthesisEvent { int32_t event_type; ExternError* error_ptr; int64_t len; uint8_t* data; } SynthesisEvent;
@@ -69,16 +75,12 @@ std::vector<std::string> split_sentences(const char* text) {
     return out;
 }
 
-// AudioSamples::to_i16_vec / as_wave_bytes (audio/ops/src/samples.rs:51-78)
-SynthesisEvent speech_event(const float* s, size_t n) {
+// event carrying i16 PCM (+ appended silence as zero samples: zeros do not move the peak normalisation)
+SynthesisEvent speech_event(const std::vector<int16_t>& pcm, size_t silence_samples) {
+    const size_t n = pcm.size() + silence_samples;
     SynthesisEvent ev{SYNTH_EVENT_SPEECH, nullptr, (int64_t)(2 * n), (uint8_t*)malloc(2 * n + 2)};
-    if (n == 0) return ev;
-    float mx = s[0], mn = s[0];
-    for (size_t i = 1; i < n; i++) { mx = fmaxf(mx, s[i]); mn = fminf(mn, s[i]); }
-    const float abs_max = fmaxf(fmaxf(fabsf(mx), fabsf(mn)), 1.1920929e-07f);
-    const float scale = 32767.0f / abs_max;
-    int16_t* o = reinterpret_cast<int16_t*>(ev.data);
-    for (size_t i = 0; i < n; i++) o[i] = (int16_t)fminf(fmaxf(s[i] * scale, -32768.0f), 32767.0f);
+    if (!pcm.empty()) memcpy(ev.data, pcm.data(), 2 * pcm.size());
+    if (silence_samples) memset(ev.data + 2 * pcm.size(), 0, 2 * silence_samples);
     return ev;
 }
 SynthesisEvent error_event(int code, const std::string& m) {
@@ -95,49 +97,35 @@ void check_output_config(const SynthesisParams& p) {
         throw Error(OPERATION_ERROR, "Sonic Error: rate / pitch modification is CPU post-processing outside libsonata_b200 "
                                      "(use rate=10, pitch=50, and length_scale for speed)");
 }
-void post_process(std::vector<float>& s, const SynthesisParams& p, int sample_rate, bool append_silence) {
-    if (append_silence) s.resize(s.size() + (size_t)p.appended_silence_ms * sample_rate / 1000, 0.f);
-    const float vol = p.volume / 100.0f;
-    for (float& x : s) x *= vol;
-}
+float gain_of(const SynthesisParams& p) { return p.volume / 100.0f; }
+size_t silence_of(const SynthesisParams& p, int sample_rate) { return (size_t)p.appended_silence_ms * sample_rate / 1000; }
 
-std::vector<std::vector<float>> speak_sentences(Voice* v, const std::vector<std::string>& ph) {
+// one batched pass over the sentences; per-sentence peak-normalised PCM converted on the device
+std::vector<std::vector<int16_t>> speak_sentences_pcm(Voice* v, const std::vector<std::string>& ph, float gain) {
     std::vector<long long> ids; std::vector<size_t> offs{0};
     for (auto& s : ph) { auto r = v->phonemes_to_ids(s.c_str()); ids.insert(ids.end(), r.begin(), r.end()); offs.push_back(ids.size()); }
     std::unique_ptr<Job> j(create_job(v, ids.data(), offs.data(), ph.size(), nullptr, nullptr, nullptr, false));
     j->run(nullptr, 0);
-    std::vector<float> all((size_t)j->total_samples);
-    SB_CUDA(cudaMemcpy(all.data(), j->d_wav, all.size() * 4, cudaMemcpyDeviceToHost));
-    std::vector<std::vector<float>> out;
-    for (size_t b = 0; b < ph.size(); b++)
-        out.emplace_back(all.begin() + j->fsegs[b].out_off, all.begin() + j->fsegs[b].out_off + (size_t)j->y_len[b] * v->a.hop());
+    std::vector<std::vector<int16_t>> out;
+    job_pcm16(*j, gain, out);
     return out;
 }
 
-void crossfade(std::vector<float>& s, size_t fade) {   // samples.rs:144-157
-    const size_t n = std::min(fade, s.size() / 2);
-    if (n == 0) return;
-    const float att = (float)(n - 1);
-    for (size_t i = 0; i < n; i++) {
-        const float f = sinf(((float)i / att) * 3.14159265358979f / 2.0f);
-        s[i] *= f; s[s.size() - i - 1] *= f;
-    }
-}
-
 // returns false when the callback asked to stop
-bool emit(const SynthesisParams& p, std::vector<float>& s, int sr, bool append_silence) {
-    post_process(s, p, sr, append_silence);
-    return p.callback(speech_event(s.data(), s.size())) == 0;
+bool emit(const SynthesisParams& p, const std::vector<int16_t>& pcm, size_t silence) {
+    return p.callback(speech_event(pcm, silence)) == 0;
 }
 
 void do_synthesize(Voice* v, const std::string& text, const SynthesisParams& p) {
     check_output_config(p);
     const std::vector<std::string> ph = split_sentences(text.c_str());
     const int sr = v->sample_rate;
+    const float gain = gain_of(p);
+    const size_t sil = silence_of(p, sr);
     if (p.mode == SYNTH_MODE_LAZY) {
-        for (auto& s : ph) { auto w = speak_sentences(v, {s}); if (!emit(p, w[0], sr, true)) return; }
+        for (auto& s : ph) { auto w = speak_sentences_pcm(v, {s}, gain); if (!emit(p, w[0], sil)) return; }
     } else if (p.mode == SYNTH_MODE_PARALLEL) {
-        if (!ph.empty()) { auto ws = speak_sentences(v, ph); for (auto& w : ws) if (!emit(p, w, sr, true)) return; }
+        if (!ph.empty()) { auto ws = speak_sentences_pcm(v, ph, gain); for (auto& w : ws) if (!emit(p, w, sil)) return; }
     } else if (p.mode == SYNTH_MODE_REALTIME) {
         long long chunk = 72; const long long pad = 3; long long produced = 0;
         for (auto& s : ph) {
@@ -146,9 +134,10 @@ void do_synthesize(Voice* v, const std::string& text, const SynthesisParams& p) 
             std::unique_ptr<Latent> z(encode_latent(v, ids.data(), ids.size()));
             const long long frames = z->frames;
             long long n = 0;
+            std::vector<int16_t> w;
             if (frames <= 2 * chunk + 2 * pad) {                                    // one-shot (piper :785)
-                std::vector<float> w; decode_latent_chunk(v, z.get(), 0, frames, w, nullptr);
-                n = 1; if (!emit(p, w, sr, false)) return;
+                decode_latent_chunk_pcm(v, z.get(), 0, frames, 0, 0, 0, gain, w, nullptr);
+                n = 1; if (!emit(p, w, 0)) return;
             } else {                                                                // AdaptiveMelChunker (piper :886-912)
                 long long last = 0, step = 1; bool more = true;
                 while (more) {
@@ -158,29 +147,54 @@ void do_synthesize(Voice* v, const std::string& text, const SynthesisParams& p) 
                     long long end = cend, epad = pad;
                     if (frames - cend <= 44) { end = frames; epad = 0; more = false; }
                     step++; last = cend;
-                    std::vector<float> w; decode_latent_chunk(v, z.get(), start, end, w, nullptr);
-                    std::vector<float> cut(w.begin() + spad * 256, w.end() - epad * 256);
-                    crossfade(cut, 42);
-                    n++; if (!emit(p, cut, sr, false)) return;
+                    decode_latent_chunk_pcm(v, z.get(), start, end, spad, epad, 42, gain, w, nullptr);   // trim + crossfade(42)
+                    n++; if (!emit(p, w, 0)) return;
                 }
             }
             produced += n;
-            if (p.appended_silence_ms) { std::vector<float> sil; if (!emit(p, sil, sr, true)) return; }
+            if (p.appended_silence_ms) { std::vector<int16_t> none; if (!emit(p, none, sil)) return; }
         }
     } else throw Error(INVALID_SYNTHESIS_MODE, "Invalid synthesis mode");
     p.callback(finished_event());
 }
 
-void write_wav_i16(const char* path, const float* s, size_t n, int sr) {
-    SynthesisEvent ev = speech_event(s, n);     // whole-buffer peak normalisation like to_i16_vec
+// whole-file peak normalisation like Audio::save_to_file -> to_i16_vec over the concatenated sentences
+void write_wav_f32(const char* path, const float* s, size_t n, int sr) {
+    std::vector<int16_t> pcm(n);
+    if (n) {
+        float mx = s[0], mn = s[0];
+        for (size_t i = 1; i < n; i++) { mx = fmaxf(mx, s[i]); mn = fminf(mn, s[i]); }
+        const float abs_max = fmaxf(fmaxf(fabsf(mx), fabsf(mn)), 1.1920929e-07f);
+        const float scale = 32767.0f / abs_max;
+        for (size_t i = 0; i < n; i++) pcm[i] = (int16_t)fminf(fmaxf(s[i] * scale, -32768.0f), 32767.0f);
+    }
     FILE* f = fopen(path, "wb");
-    if (!f) { free(ev.data); throw Error(OPERATION_ERROR, std::string("cannot open `") + path + "` for writing"); }
+    if (!f) throw Error(OPERATION_ERROR, std::string("cannot open `") + path + "` for writing");
     const uint32_t bytes = (uint32_t)(2 * n), riff = 36 + bytes, fmt = 16, br = (uint32_t)sr * 2;
-    const uint16_t pcm = 1, ch = 1, ba = 2, bits = 16;
+    const uint16_t pcmf = 1, ch = 1, ba = 2, bits = 16;
     fwrite("RIFF", 1, 4, f); fwrite(&riff, 4, 1, f); fwrite("WAVEfmt ", 1, 8, f); fwrite(&fmt, 4, 1, f);
-    fwrite(&pcm, 2, 1, f); fwrite(&ch, 2, 1, f); fwrite(&sr, 4, 1, f); fwrite(&br, 4, 1, f); fwrite(&ba, 2, 1, f);
-    fwrite(&bits, 2, 1, f); fwrite("data", 1, 4, f); fwrite(&bytes, 4, 1, f); fwrite(ev.data, 1, bytes, f);
-    fclose(f); free(ev.data);
+    fwrite(&pcmf, 2, 1, f); fwrite(&ch, 2, 1, f); fwrite(&sr, 4, 1, f); fwrite(&br, 4, 1, f); fwrite(&ba, 2, 1, f);
+    fwrite(&bits, 2, 1, f); fwrite("data", 1, 4, f); fwrite(&bytes, 4, 1, f); fwrite(pcm.data(), 1, bytes, f);
+    fclose(f);
+}
+
+// f32 waveforms of one batched pass through the context's page-locked staging (speak-to-file: the file is normalised
+// as a whole, so the per-sentence device conversion does not apply)
+std::vector<std::vector<float>> speak_sentences_f32(Voice* v, const std::vector<std::string>& ph) {
+    std::vector<long long> ids; std::vector<size_t> offs{0};
+    for (auto& s : ph) { auto r = v->phonemes_to_ids(s.c_str()); ids.insert(ids.end(), r.begin(), r.end()); offs.push_back(ids.size()); }
+    std::unique_ptr<Job> j(create_job(v, ids.data(), offs.data(), ph.size(), nullptr, nullptr, nullptr, false));
+    j->run(nullptr, 0);
+    Context& C = *j->ctx;
+    const size_t bytes = (size_t)j->total_samples * 4;
+    C.ensure_pin(bytes + 4096);
+    SB_CUDA(cudaMemcpyAsync(C.pin, j->d_wav, bytes, cudaMemcpyDeviceToHost, C.stream));
+    SB_CUDA(cudaStreamSynchronize(C.stream));
+    const float* all = reinterpret_cast<const float*>(C.pin);
+    std::vector<std::vector<float>> out;
+    for (size_t b = 0; b < ph.size(); b++)
+        out.emplace_back(all + j->fsegs[b].out_off, all + j->fsegs[b].out_off + (size_t)j->y_len[b] * v->a.hop());
+    return out;
 }
 
 }  // namespace
@@ -196,11 +210,12 @@ SonataVoice* libsonataLoadVoiceFromConfigPath(const char* config_path_ptr, Exter
     guarded(out_error, [&] {
         if (!config_path_ptr) throw Error(INVALID_UTF8_SEQUENCE, "Invalid utf-8 input.");
         const char* d = getenv("SONATA_B200_DEVICE");
-        r = new SonataVoice{load_voice(config_path_ptr, d ? atoi(d) : 0)};
+        r = new SonataVoice{std::shared_ptr<Voice>(load_voice(config_path_ptr, d ? atoi(d) : 0))};
     });
     return r;
 }
-void libsonataUnloadSonataVoice(SonataVoice* voice_ptr) { if (voice_ptr) { delete voice_ptr->v; delete voice_ptr; } }
+// drops this handle's reference; a synthesis still running on a worker thread keeps the voice alive until it returns
+void libsonataUnloadSonataVoice(SonataVoice* voice_ptr) { delete voice_ptr; }
 
 void libsonataGetAudioInfo(SonataVoice* voice_ptr, AudioInfo* info, ExternError* out_error) {
     guarded(out_error, [&] { info->sample_rate = (uint32_t)voice_ptr->v->sample_rate; info->num_channels = 1; info->sample_width = 2; });
@@ -216,7 +231,7 @@ PiperSynthConfig* libsonataGetPiperDefaultSynthConfig(SonataVoice* voice_ptr, Ex
 }
 void libsonataSetPiperSynthConfig(SonataVoice* voice_ptr, PiperSynthConfig c, ExternError* out_error) {
     guarded(out_error, [&] {   // capi always passes Some(speaker) (capi/src/lib.rs:175-184) -> unknown ids are errors
-        Voice* v = voice_ptr->v;
+        Voice* v = voice_ptr->v.get();
         std::unique_lock<std::shared_mutex> g(v->cfg_mu);
         v->cfg.length_scale = c.length_scale; v->cfg.noise_scale = c.noise_scale; v->cfg.noise_w = c.noise_w;
         bool found = false;
@@ -229,16 +244,17 @@ void libsonataSetPiperSynthConfig(SonataVoice* voice_ptr, PiperSynthConfig c, Ex
 void libsonataSpeak(SonataVoice* voice_ptr, const char* text_ptr, SynthesisParams params, ExternError* out_error) {
     guarded(out_error, [&] {
         if (!text_ptr) throw Error(INVALID_UTF8_SEQUENCE, "Invalid utf-8 input.");
-        Voice* v = voice_ptr->v;
+        std::shared_ptr<Voice> v = voice_ptr->v;
         const std::string text(text_ptr);
         if (params.nonblocking) {
-            std::thread([v, text, params] {                      // callback fires on a foreign thread (capi :374-381)
-                try { do_synthesize(v, text, params); }
+            std::thread([v, text, params] {                      // callback fires on a foreign thread (capi :374-381);
+                try { do_synthesize(v.get(), text, params); }    // the thread owns a reference to the voice
                 catch (const Error& e) { params.callback(error_event(e.code, e.what())); }
                 catch (const std::exception& e) { params.callback(error_event(UNKNOWN_ERROR, e.what())); }
+                catch (...) { params.callback(error_event(UNKNOWN_ERROR, "unknown error")); }
             }).detach();
         } else {
-            try { do_synthesize(v, text, params); }
+            try { do_synthesize(v.get(), text, params); }
             catch (const Error& e) {
                 if (e.code == INVALID_SYNTHESIS_MODE || e.code == INVALID_UTF8_SEQUENCE) throw;
                 params.callback(error_event(e.code, e.what()));  // stream errors arrive as events (capi :428-432)
@@ -254,12 +270,17 @@ uint8_t libsonataSpeakToFile(SonataVoice* voice_ptr, const char* text_ptr, Synth
         try {
             if (!text_ptr || !out_filename_ptr) throw Error(INVALID_UTF8_SEQUENCE, "Invalid utf-8 input.");
             check_output_config(params);
-            Voice* v = voice_ptr->v;
+            Voice* v = voice_ptr->v.get();
             auto ph = split_sentences(text_ptr);
             std::vector<float> all;
-            if (!ph.empty()) for (auto& w : speak_sentences(v, ph)) { post_process(w, params, v->sample_rate, true); all.insert(all.end(), w.begin(), w.end()); }
+            const float vol = gain_of(params);
+            if (!ph.empty()) for (auto& w : speak_sentences_f32(v, ph)) {
+                w.resize(w.size() + silence_of(params, v->sample_rate), 0.f);
+                for (float& x : w) x *= vol;
+                all.insert(all.end(), w.begin(), w.end());
+            }
             if (all.empty()) throw Error(OPERATION_ERROR, "No speech data to write");
-            write_wav_i16(out_filename_ptr, all.data(), all.size(), v->sample_rate);
+            write_wav_f32(out_filename_ptr, all.data(), all.size(), v->sample_rate);
             ok = 1;
         } catch (const std::exception&) { ok = 0; }
     });

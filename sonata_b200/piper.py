@@ -114,6 +114,17 @@ class _VitsCommons:
         _check(lib.sb200_voice_load(str(config_path).encode("utf-8"), device, C.byref(self._h), C.byref(err)), err)
         self.config_path = str(config_path)
         self.device = device
+        self._speakers = None
+
+    def get_speakers(self) -> Optional[dict]:
+        """SonataModel::get_speakers (piper/src/lib.rs:463-465): {speaker id: name} of a multi-speaker voice, read from
+        the `speaker_id_map` of the voice config (None for single-speaker voices)."""
+        if self._speakers is None:
+            import json
+            with open(self.config_path, encoding="utf-8") as f:
+                m = json.load(f).get("speaker_id_map") or {}
+            self._speakers = {int(v): k for k, v in m.items()}
+        return self._speakers or None
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:

@@ -110,6 +110,63 @@ def test_facade_speak_modes(lib_built, voice_paths, tmp_path):
     # invalid mode -> INVALID_SYNTHESIS_MODE through out_error
     lib.libsonataSpeak(v, text, SynthesisParams(7, 10, 100, 50, 0, CALLBACK(cb), 0), C.byref(err))
     assert err.code == 16
+    # ---- the device post-path (volume gain, crossfade, peak normalisation, i16) is bit-identical to the host mirror of the
+    # reference arithmetic (samples.rs:51-78, 144-157; synth/src/lib.rs:84-86, 106-113) applied to the f32 result
+    import sonata_b200
+    from sonata_b200 import PiperSynthesisConfig
+    m = sonata_b200.from_config_path(voice_paths["medium"], device=0)
+    m.set_fallback_synthesis_config(PiperSynthesisConfig(None, 0.0, 1.0, 0.0))      # the facade voice got the same scales above
+    sents = text.decode("utf-8").split("\n")
+    sil = 30 * 22050 // 1000
+    events.clear()
+    lib.libsonataSpeak(v, text, SynthesisParams(1, 10, 80, 50, 30, CALLBACK(cb), 0), C.byref(err))
+    got = [e[1] for e in events[:-1]]
+    vol = np.float32(80 / 100.0)
+    for g_, a_ in zip(got, m.speak_batch(sents)):
+        x = np.concatenate([a_.samples.as_slice() * vol, np.zeros(sil, dtype=np.float32)])
+        assert np.array_equal(g_, sonata_b200.AudioSamples(x).to_i16_vec())
+    # realtime: the reference chunk schedule (72, 3), overlap trim and crossfade(42), chunk by chunk
+    m.close()
+    import json
+    cfgd = json.load(open(voice_paths["medium"], encoding="utf-8"))
+    cfgd["streaming"] = True
+    json.dump(cfgd, open(tmp_path / "rt.onnx.json", "w", encoding="utf-8"), ensure_ascii=False)
+    os.symlink(voice_paths["medium"].replace(".onnx.json", ".svw"), tmp_path / "rt.svw")
+    ms = sonata_b200.from_config_path(str(tmp_path / "rt.onnx.json"), device=0)
+    ms.set_fallback_synthesis_config(PiperSynthesisConfig(None, 0.0, 1.0, 0.0))
+    events.clear()
+    lib.libsonataSpeak(v, text, SynthesisParams(2, 10, 100, 50, 0, CALLBACK(cb), 0), C.byref(err))
+    got = [e[1] for e in events[:-1]]
+    exp, chunk, produced = [], 72, 0
+    for s in sents:
+        if produced:
+            chunk = chunk * 1 * produced
+        chunks = list(ms.stream_synthesis(s, chunk, 3))
+        exp += [c.to_i16_vec() for c in chunks]
+        produced += len(chunks)
+    assert len(got) == len(exp) and len(exp) > len(sents)
+    for g_, e_ in zip(got, exp):
+        # the 2 x 42 faded samples go through sinf (libm in the library, numpy's float32 sin in the mirror): allow one
+        # LSB there, everything else is bit-identical
+        assert g_.shape == e_.shape
+        d = np.abs(g_.astype(np.int32) - e_.astype(np.int32))
+        assert d.max() <= 1 and int((d != 0).sum()) <= 84 and not d[42:-42].any()
+    ms.close()
+    # ---- a non-blocking speak keeps the voice alive after unload (the reference clones the Arc, capi/src/lib.rs:314,375)
+    import threading
+    v2 = lib.libsonataLoadVoiceFromConfigPath(voice_paths["medium"].encode(), C.byref(err))
+    done, seen = threading.Event(), []
+
+    def cb2(ev):
+        seen.append(ev.event_type)
+        lib.libsonataFreeSynthesisEvent(ev)
+        if ev.event_type != 0:
+            done.set()
+        return 0
+    cb2_c = CALLBACK(cb2)
+    lib.libsonataSpeak(v2, text, SynthesisParams(0, 10, 100, 50, 0, cb2_c, 1), C.byref(err))
+    lib.libsonataUnloadSonataVoice(v2)                                             # while the worker thread is synthesising
+    assert done.wait(60) and seen[-1] == 1 and seen.count(0) == len(sents)
     out = tmp_path / "o.wav"
     ok = lib.libsonataSpeakToFile(v, text, SynthesisParams(1, 10, 100, 50, 50, CALLBACK(cb), 0), str(out).encode(), C.byref(err))
     assert ok == 1 and os.path.getsize(out) == 44 + 2 * (totals[1] + 2 * (50 * 22050 // 1000))
