@@ -274,9 +274,20 @@ def _conv_flow_reverse(W, p, z, g, a, calib=None, stages=None):
     return torch.cat([z0, z1], 1)
 
 
-def sdp_reverse(W, x, eps_w, noise_w, a, calib=None, stages=None):
-    """dp(x, reverse=True): x[1,H,T], eps_w[1,2,T] ~ N(0,1) -> logw[1,1,T]."""
+def speaker_embedding(W, sid):
+    """g = emb_g(sid).unsqueeze(-1) for multi-speaker voices (SynthesizerTrn.infer; the reference feeds `sid` only when
+    num_speakers > 1, piper/src/lib.rs:353-358); None for single-speaker voices."""
+    if "emb_g.weight" not in W:
+        return None
+    return W["emb_g.weight"][int(sid or 0)].view(1, -1, 1)
+
+
+def sdp_reverse(W, x, eps_w, noise_w, a, calib=None, stages=None, g=None):
+    """dp(x, reverse=True): x[1,H,T], eps_w[1,2,T] ~ N(0,1) -> logw[1,1,T].  g: speaker embedding [1,gin,1] or None
+    (StochasticDurationPredictor: x = pre(x) + cond(g))."""
     h = _conv(W, "dp.pre", x, calib)
+    if g is not None:
+        h = h + _conv(W, "dp.cond", g, calib)
     h = _dds(W, "dp.convs.", h, a, calib=calib)
     h = _conv(W, "dp.proj", h, calib)
     z = eps_w * noise_w
@@ -318,12 +329,15 @@ def expand(m_p, logs_p, w_ceil, y_len, eps_z, noise_scale):
 
 
 # --------------------------------------------------------------------------- flow
-def _wn(W, p, x, a, calib=None):
+def _wn(W, p, x, a, calib=None, g=None):
     H, k = a["hidden"], a["flow_kernel"]
     out = torch.zeros_like(x)
     n = a["wn_layers"]
+    gc = _conv(W, p + "cond_layer", g, calib) if g is not None else None      # modules.WN: all layers' conditioning at once
     for l in range(n):
         x_in = _conv(W, p + f"in_layers.{l}", x, calib, padding=(k - 1) // 2)
+        if gc is not None:
+            x_in = x_in + gc[:, 2 * H * l:2 * H * (l + 1)]
         acts = torch.tanh(x_in[:, :H]) * torch.sigmoid(x_in[:, H:])
         rs = _conv(W, p + f"res_skip_layers.{l}", acts, calib)
         if l < n - 1:
@@ -334,14 +348,14 @@ def _wn(W, p, x, a, calib=None):
     return out
 
 
-def flow_reverse(W, z, a, calib=None, stages=None):
+def flow_reverse(W, z, a, calib=None, stages=None, g=None):
     half = a["inter"] // 2
     for f in reversed(range(a["flow_n"])):
         z = torch.flip(z, [1])
         p = f"flow.flows.{2 * f}."
         x0, x1 = torch.split(z, [half, half], 1)
         h = _conv(W, p + "pre", x0, calib)
-        h = _wn(W, p + "enc.", h, a, calib)
+        h = _wn(W, p + "enc.", h, a, calib, g=g)
         m = _conv(W, p + "post", h, calib)
         x1 = x1 - m
         z = torch.cat([x0, x1], 1)
@@ -351,8 +365,10 @@ def flow_reverse(W, z, a, calib=None, stages=None):
 
 
 # --------------------------------------------------------------------------- HiFi-GAN
-def decoder(W, z, a, calib=None, stages=None):
+def decoder(W, z, a, calib=None, stages=None, g=None):
     x = _conv(W, "dec.conv_pre", z, calib, padding=3)
+    if g is not None:
+        x = x + _conv(W, "dec.cond", g, calib)
     if stages is not None:
         stages["dec.pre"] = x
     nk = len(a["res_kernels"])
@@ -397,7 +413,7 @@ def decoder(W, z, a, calib=None, stages=None):
 
 
 # --------------------------------------------------------------------------- whole path
-def encode(W, ids, scales, eps_w=None, eps_z=None, calib=None, stages=None):
+def encode(W, ids, scales, eps_w=None, eps_z=None, calib=None, stages=None, sid=None):
     """Streaming 'encoder.onnx' half: ids -> z[1,I,T_y] (piper/src/lib.rs:537-574).
     scales = [noise_scale, length_scale, noise_w] (piper/src/lib.rs:348-352)."""
     a = arch_of(W)
@@ -410,29 +426,31 @@ def encode(W, ids, scales, eps_w=None, eps_z=None, calib=None, stages=None):
         eps_w = torch.zeros(1, 2, T, dtype=dt)
     else:
         eps_w = torch.as_tensor(eps_w).to(dt).view(1, 2, T)
-    logw = sdp_reverse(W, x, eps_w, noise_w, a, calib, stages)
+    g = speaker_embedding(W, sid)
+    logw = sdp_reverse(W, x, eps_w, noise_w, a, calib, stages, g=g)
     w, w_ceil, y_len = durations(logw, length_scale)
     if eps_z is not None:
         eps_z = torch.as_tensor(eps_z).to(dt).view(1, a["inter"], y_len)
     z_p, tok = expand(m_p, logs_p, w_ceil, y_len, eps_z, noise_scale)
-    z = flow_reverse(W, z_p, a, calib, stages)
+    z = flow_reverse(W, z_p, a, calib, stages, g=g)
     if stages is not None:
         stages.update({"x": x, "m_p": m_p, "logs_p": logs_p, "logw": logw, "w": w,
                        "w_ceil": w_ceil, "y_len": y_len, "z_p": z_p, "z": z, "tok": tok})
     return z
 
 
-def decode(W, z, calib=None, stages=None):
-    """Streaming 'decoder.onnx' half: z[1,I,T] -> wav[1,1,256*T] (piper/src/lib.rs:736-762)."""
-    return decoder(W, z, arch_of(W), calib, stages)
+def decode(W, z, calib=None, stages=None, sid=None):
+    """Streaming 'decoder.onnx' half: z[1,I,T] -> wav[1,1,256*T] (piper/src/lib.rs:736-762; multi-speaker voices also
+    pass the encoder's `g` output, :706-735)."""
+    return decoder(W, z, arch_of(W), calib, stages, g=speaker_embedding(W, sid))
 
 
-def infer(W, ids, scales, eps_w=None, eps_z=None, calib=None, stages=None):
+def infer(W, ids, scales, eps_w=None, eps_z=None, calib=None, stages=None, sid=None):
     """ids (list of i64), scales f32[3] -> waveform float array, as read from ``outputs[0]``
     at piper/src/lib.rs:382-392."""
     with torch.inference_mode(calib is None):
-        z = encode(W, ids, scales, eps_w, eps_z, calib, stages)
-        wav = decode(W, z, calib, stages)
+        z = encode(W, ids, scales, eps_w, eps_z, calib, stages, sid=sid)
+        wav = decode(W, z, calib, stages, sid=sid)
         if stages is not None:
             stages["wav"] = wav
     return wav.reshape(-1)

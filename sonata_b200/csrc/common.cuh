@@ -160,6 +160,8 @@ void launch_i16(const float* wav, const FrameSeg* fsegs, int nseg, int hop, long
 void launch_randn(float* out, long long n, unsigned long long seed, unsigned long long stream_id, cudaStream_t st);
 void launch_scale_copy2(const float* eps, float s, float* z, RowMap map, cudaStream_t st);   // z[r][0..1] = eps*s
 void launch_fill_zero(float* p, long long n, cudaStream_t st);
+// out[r] = base[r] + sum_k w[r][k] * g[k]   (speaker conditioning: effective biases of the conditioned convs)
+void launch_cond_bias(const float* w, const float* base, const float* g, int rows, int gin, float* out, cudaStream_t st);
 
 // launch-configuration errors are not sticky and would otherwise be lost: throw immediately
 void check_launch(const char* what);

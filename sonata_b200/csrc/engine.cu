@@ -191,10 +191,12 @@ struct Runner {
         bool tf_ok = false;    // duration-critical layer: tcgen05 3xTF32 with chunk-flushed accumulation (conv_tf.cu)
         float* yt = nullptr; int yt_col0 = 0, ldyt = 0;     // conv_tf only: column tiles >= yt_col0 stored transposed
     };
+    // bias of a conv: the voice's, or this call's speaker-conditioned one (multi-speaker voices)
+    const float* bias_of(const ConvW& w) const { return (j.d_cond && w.cond_off >= 0) ? j.d_cond + w.cond_off : w.bias; }
     void conv(const ConvW& w, const float* x, int ldx, const Level& lin, const Opt& o) {
         ConvArgs p{};
         p.x = x; p.ldx = ldx; p.rows_in = lin.map.rows; p.cin = w.cin; p.in_slope = o.in_slope;
-        p.w = w.w; p.bias = w.bias; p.ldw = w.ldw; p.cout = w.cout; p.wtc = w.wtc; p.tc_nt = w.tc_nt; p.wts = w.wts; p.wcat = w.wcat; p.wtf = w.wtf;
+        p.w = w.w; p.bias = bias_of(w); p.ldw = w.ldw; p.cout = w.cout; p.wtc = w.wtc; p.tc_nt = w.tc_nt; p.wts = w.wts; p.wcat = w.wcat; p.wtf = w.wtf;
         p.ntaps = w.ntaps; memcpy(p.tap_off, w.tap_off, sizeof(p.tap_off)); p.min_off = w.min_off; p.span = w.span;
         p.rows_q = lin.map.rows; p.orow_mul = o.orow_mul; p.orow_add = o.orow_add;
         p.map = lin.map;
@@ -397,7 +399,7 @@ void Job::run(float* d_out, size_t d_out_cap) {
     const size_t xfloats = (size_t)RX * (H * 10 + F + 2 * I + 32 + 2 + 2 + 1) +
                            (tc_att ? (size_t)a.heads * RX * att_tp + 2 * (size_t)RX * H : 0);
     const size_t tile_bytes = (tiles_s.size() + tiles_o.size()) * sizeof(TfTile);
-    const size_t p1_bytes = xfloats * 4 + (size_t)RX * 20 + B * 64 + tile_bytes + (1 << 20) +
+    const size_t p1_bytes = xfloats * 4 + (size_t)RX * 20 + B * 64 + tile_bytes + (1 << 20) + (size_t)V.cond_rows * 4 + 1024 +
                             (debug ? (size_t)RX * (4 * H + att_tp) * 4 + 4096 : 0);
     // The arena must also hold phase 2; sizes are only known after the durations come back, so phase 1
     // runs in the front of the arena and phase 2 re-plans behind it (growing = realloc would lose phase-1
@@ -489,6 +491,15 @@ void Job::run(float* d_out, size_t d_out_cap) {
         } else {
             launch_randn(d_epsw, (long long)RX * 2, V.noise_seed, 2 * noise_call, st);
         }
+    }
+
+    // ---------------- speaker conditioning (multi-speaker voices) ----------------
+    d_cond = nullptr;
+    if (V.num_speakers > 1) {
+        const long long sid = cfg.has_speaker ? cfg.speaker : 0;      // piper/src/lib.rs:353-358: speaker.unwrap_or(0)
+        if (sid < 0 || sid >= V.emb_rows) throw Error(19, "Failed to run model inference. Error: speaker id out of range");
+        d_cond = C.dev.get<float>((size_t)V.cond_rows);
+        launch_cond_bias(V.cond_w, V.cond_base, V.emb_g + (size_t)sid * V.gin, V.cond_rows, V.gin, d_cond, st);
     }
 
     // ---------------- text encoder ----------------
@@ -587,7 +598,7 @@ void Job::run(float* d_out, size_t d_out_cap) {
             SB_CUDA(cudaStreamSynchronize(st));
             const ptrdiff_t delta = C.dev.base - old.base;
             auto mv = [&](auto*& ptr) { if (ptr) ptr = reinterpret_cast<std::remove_reference_t<decltype(ptr)>>(reinterpret_cast<char*>(ptr) + delta); };
-            mv(d_ids_rows); mv(d_xend); mv(d_xsegs); mv(d_cum); mv(d_ylen); mv(d_epsw); mv(d_xseg_of_gran); mv(d_tiles_s); mv(d_tiles_o);
+            mv(d_ids_rows); mv(d_xend); mv(d_xsegs); mv(d_cum); mv(d_ylen); mv(d_epsw); mv(d_xseg_of_gran); mv(d_tiles_s); mv(d_tiles_o); mv(d_cond);
             mv(xa); mv(stats); mv(logw);
             for (auto& kv : dbg) kv.second.first = reinterpret_cast<float*>(reinterpret_cast<char*>(kv.second.first) + delta);
             SB_CUDA(cudaFree(old.base));
@@ -678,6 +689,7 @@ Latent* encode_latent(Voice* v, const long long* ids, size_t n) {
     j->run(nullptr, 0);
     std::unique_ptr<Latent> L(new Latent());
     L->v = v; L->frames = j->y_len[0];
+    L->sid = j->cfg.has_speaker ? j->cfg.speaker : 0;
     const size_t bytes = (size_t)L->frames * v->a.inter * 4;
     SB_CUDA(cudaMalloc(&L->z, bytes));
     const float* src = j->z_dev + (size_t)j->fsegs[0].off * v->a.inter;
@@ -695,13 +707,18 @@ float* decode_chunk_device(Voice* v, const Latent* z, long long lo, long long hi
     SB_CUDA(cudaSetDevice(v->device));
     const int n = (int)(hi - lo);
     const int RY = round_up(n + HY, GY);
-    C.ensure_dev(decoder_bytes(*v, RY, false) + (size_t)RY * a.inter * 4 + (size_t)n * a.hop() * 4 + extra_bytes + (4 << 20));
+    C.ensure_dev(decoder_bytes(*v, RY, false) + (size_t)RY * a.inter * 4 + (size_t)n * a.hop() * 4 + extra_bytes + (size_t)v->cond_rows * 4 + (4 << 20));
     C.ensure_pin(std::max<size_t>(1 << 20, (size_t)n * a.hop() * 4 + 4096));
     C.dev.used = 0; C.events_used = 0;
     if (!C.ev_begin) { SB_CUDA(cudaEventCreate(&C.ev_begin)); SB_CUDA(cudaEventCreate(&C.ev_end)); }
     cudaStream_t st = C.stream;
     Runner R(j);
     SB_CUDA(cudaEventRecord(C.ev_begin, st));
+    if (v->num_speakers > 1) {       // decoder.onnx takes the encoder's `g` (piper/src/lib.rs:706-735, 739-743)
+        if (z->sid < 0 || z->sid >= v->emb_rows) throw Error(19, "Failed to run model inference. Error: speaker id out of range");
+        j.d_cond = C.dev.get<float>((size_t)v->cond_rows);
+        launch_cond_bias(v->cond_w, v->cond_base, v->emb_g + (size_t)z->sid * v->gin, v->cond_rows, v->gin, j.d_cond, st);
+    }
     Level LY = build_y_layout(j, C, st, std::vector<int>{n}, a.hop());
     float* s = C.dev.get<float>((size_t)RY * a.inter);
     launch_fill_zero(s, (long long)RY * a.inter, st);

@@ -53,6 +53,7 @@ struct ConvW {
     float* wcat = nullptr;                   // hi/lo-stacked tap-pair images (conv_tc.cu cat mode), column tiles <= 64
     float* wtf = nullptr;                    // tf32 hi/lo images (conv_tf.cu): text-encoder / duration-predictor layers
     int cin = 0, cout = 0, ldw = 0, ntaps = 0;
+    int cond_off = -1;                       // multi-speaker voices: offset of this conv's per-call effective bias (Job::d_cond)
     int tap_off[SB_MAX_TAPS] = {0};
     int min_off = 0, span = 0;
 };
@@ -95,6 +96,9 @@ struct Voice {
     std::vector<CouplingW> flows;   // in application order (f = n-1 .. 0)
     ConvW conv_pre;
     std::vector<UpStageW> ups;
+    // multi-speaker conditioning (num_speakers > 1): see the end of load_voice
+    float* emb_g = nullptr; int gin = 0, emb_rows = 0;
+    float *cond_w = nullptr, *cond_base = nullptr; int cond_rows = 0;
     float* conv_post_w = nullptr;   // [7][C_last]
     int c_last = 0;
     size_t weight_bytes = 0;
@@ -176,6 +180,7 @@ struct Job {
     int* d_xseg_of_gran = nullptr; TfTile *d_tiles_s = nullptr, *d_tiles_o = nullptr;
     float *d_epsw = nullptr, *d_epsz = nullptr;
     float* d_wav = nullptr; bool wav_external = false;
+    float* d_cond = nullptr;       // effective biases of the speaker-conditioned convs for this call
     std::map<std::string, std::pair<float*, int>> dbg;   // name -> (device ptr, cols)
     std::map<std::string, int> dbg_level;                // name -> U (rows per frame) or 0 for X level
     std::vector<Region> regions;
@@ -191,6 +196,7 @@ Job* create_job(Voice* v, const long long* ids, const size_t* offs, size_t B, co
 
 struct Latent {
     Voice* v = nullptr;
+    long long sid = 0;    // speaker of the encoder pass (the reference hands `g` from encoder.onnx to decoder.onnx)
     float* z = nullptr;   // device [frames][inter]
     long long frames = 0;
     ~Latent();

@@ -650,6 +650,18 @@ __global__ void randn_kernel(float* __restrict__ out, long long n, unsigned long
         if (i4 * 4 + e < n) out[i4 * 4 + e] = v[e];
 }
 
+// speaker conditioning: one warp per row of the stacked 1x1 conditioning convs
+__global__ void __launch_bounds__(256) cond_bias_kernel(const float* __restrict__ w, const float* __restrict__ base,
+                                                        const float* __restrict__ g, int rows, int gin,
+                                                        float* __restrict__ out) {
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    float s = 0.f;
+    for (int k = lane; k < gin; k += 32) s = fmaf(w[(size_t)r * gin + k], g[k], s);
+    s = warp_sum(s);
+    if (lane == 0) out[r] = base[r] + s;
+}
+
 __global__ void fill_zero_kernel(float4* p, long long n4) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n4) p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -790,6 +802,11 @@ void launch_i16(const float* wav, const FrameSeg* fsegs, int nseg, int hop, long
 void launch_randn(float* out, long long n, unsigned long long seed, unsigned long long stream_id, cudaStream_t st) {
     const long long n4 = (n + 3) / 4;
     randn_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(out, n, seed, stream_id);
+    g_launch_count++;
+}
+
+void launch_cond_bias(const float* w, const float* base, const float* g, int rows, int gin, float* out, cudaStream_t st) {
+    cond_bias_kernel<<<(rows + 7) / 8, 256, 0, st>>>(w, base, g, rows, gin, out);
     g_launch_count++;
 }
 

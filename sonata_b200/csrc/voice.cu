@@ -330,6 +330,7 @@ Voice* load_voice(const std::string& config_path, int device) {
         throw Error(17, "unsupported voice architecture");
     const int D = H / a.heads;
     if (D != 96 && D != 48) throw Error(17, "unsupported attention head size");
+    if (H != 96 && H != 192 && H != 256) throw Error(17, "unsupported hidden width (LayerNorm kernels: 96 / 192 / 256)");
 
     Uploader U{v.get()};
     U.want_tf = true;          // text encoder + duration predictor: error-compensated tf32 with chunked accumulation
@@ -479,6 +480,48 @@ Voice* load_voice(const std::string& config_path, int device) {
         for (int c = 0; c < C; c++) for (int t = 0; t < 7; t++) wt[(size_t)t * C + c] = w.f[(size_t)c * 7 + t];
         v->conv_post_w = U.up(wt);
         if (C != 16 && C != 32 && C != 64) throw Error(17, "unsupported final decoder width");
+    }
+    if (v->num_speakers > 1) {
+        // Multi-speaker voice: g = emb_g(sid) conditions the duration predictor (dp.cond), every coupling layer's WaveNet
+        // (enc.cond_layer, 2H rows per layer) and the HiFi-GAN input (dec.cond) through 1x1 convs of a [gin, 1] vector,
+        // i.e. g only adds a per-call vector to the BIAS of dp.pre, of every WaveNet in_layer and of conv_pre.  All those
+        // rows are stacked into one [rows][gin] matrix (+ base bias = conv bias + cond bias); one small kernel per call
+        // produces the effective biases (engine.cu).  Reference: `sid` input, piper/src/lib.rs:353-358.
+        const HostTensor& eg = T(m, "emb_g.weight");
+        if (eg.dims.size() != 2 || eg.dims[0] < v->num_speakers) throw Error(17, "emb_g.weight does not cover num_speakers");
+        const int G = eg.dims[1];
+        v->gin = G; v->emb_rows = eg.dims[0];
+        v->emb_g = U.up(eg.f);
+        std::vector<float> wc, base;
+        auto add = [&](ConvW& c, const HostTensor& cw, const HostTensor& cb, int row0, const std::vector<int>* perm,
+                       const std::vector<float>& conv_bias /* padded to ldw */) {
+            if (cw.dims[1] != G) throw Error(17, "conditioning layer width does not match emb_g");
+            c.cond_off = (int)base.size();
+            for (int n = 0; n < c.ldw; n++) {
+                const bool live = n < c.cout;
+                const int src = live ? row0 + (perm ? (*perm)[n] : n) : 0;
+                for (int k = 0; k < G; k++) wc.push_back(live ? cw.f[(size_t)src * G + k] : 0.f);
+                base.push_back(live ? conv_bias[n] + cb.f[src] : 0.f);
+            }
+        };
+        auto host_bias = [&](const ConvW& c) {
+            std::vector<float> b(c.ldw);
+            SB_CUDA(cudaMemcpy(b.data(), c.bias, (size_t)c.ldw * 4, cudaMemcpyDeviceToHost));
+            return b;
+        };
+        add(v->dp_pre, T(m, "dp.cond.weight"), T(m, "dp.cond.bias"), 0, nullptr, host_bias(v->dp_pre));
+        std::vector<int> gate(2 * H);
+        for (int j = 0; j < H; j++) { gate[2 * j] = j; gate[2 * j + 1] = H + j; }
+        for (int step = 0; step < a.flow_n; step++) {
+            const int f = a.flow_n - 1 - step;
+            const std::string p = "flow.flows." + std::to_string(2 * f) + ".enc.cond_layer.";
+            for (int l = 0; l < a.wn_layers; l++)
+                add(v->flows[step].in[l], T(m, p + "weight"), T(m, p + "bias"), 2 * H * l, &gate, host_bias(v->flows[step].in[l]));
+        }
+        add(v->conv_pre, T(m, "dec.cond.weight"), T(m, "dec.cond.bias"), 0, nullptr, host_bias(v->conv_pre));
+        v->cond_rows = (int)base.size();
+        v->cond_w = U.up(wc);
+        v->cond_base = U.up(base);
     }
     SB_CUDA(cudaDeviceSynchronize());
     return v.release();

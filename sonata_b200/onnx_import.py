@@ -11,7 +11,9 @@ STATUS: verified on ONNX files produced by the test-suite's own writer (tests/te
 Piper voice offline, so the assumptions about upstream's export are listed here and fail loudly when they do not hold:
   * initialisers keep their state-dict names (constant-folded weights would appear as `onnx::Conv_123`: those are
     reported as missing parameters; graph-walking to recover them is not implemented);
-  * single-speaker voices only (`emb_g` / `cond` layers are rejected);
+  * multi-speaker voices carry `emb_g.weight` [n_speakers, gin] and the conditioning convs `dp.cond`,
+    `flow.flows.<2f>.enc.cond_layer` (weight-normed) and `dec.cond` (voicegen.speaker_specs); n_speakers must agree
+    with `num_speakers` of the JSON config;
   * fp32 / fp16 / fp64 tensor payloads in `raw_data`, `float_data` or `double_data`; external data is rejected.
 """
 from __future__ import annotations
@@ -168,10 +170,13 @@ def detect_quality(t: Dict[str, np.ndarray]) -> str:
 def convert_tensors(inits: Dict[str, np.ndarray]) -> Tuple[str, Dict[str, np.ndarray]]:
     """Initialisers -> exactly the tensors of `voicegen.tensor_specs(arch)`, fp32, shapes verified."""
     t = _fold_weight_norm(inits)
-    if any(k.startswith("emb_g") for k in t):
-        raise ValueError("multi-speaker voices (`emb_g`, conditioning layers) are not supported yet")
     quality = detect_quality(t)
     specs = voicegen.tensor_specs(voicegen.ARCH[quality])
+    eg = t.get("emb_g.weight")
+    if eg is not None:                               # multi-speaker voice
+        if eg.ndim != 2 or eg.shape[1] != voicegen.GIN_CHANNELS:
+            raise ValueError(f"emb_g.weight has shape {tuple(eg.shape)}; expected [n_speakers, {voicegen.GIN_CHANNELS}]")
+        specs.update(voicegen.speaker_specs(voicegen.ARCH[quality], int(eg.shape[0])))
     out, missing, bad = {}, [], []
     for name, (shape, _kind) in specs.items():
         a = t.get(name)
@@ -195,8 +200,9 @@ def import_voice(onnx_path: str, config_path: str, out_dir: str) -> str:
     quality, tensors = convert_tensors(read_initializers(onnx_path))
     with open(config_path) as f:
         cfg = json.load(f)
-    if int(cfg.get("num_speakers", 1)) > 1:
-        raise ValueError("multi-speaker voices are not supported yet")
+    n_spk = int(tensors["emb_g.weight"].shape[0]) if "emb_g.weight" in tensors else 1
+    if int(cfg.get("num_speakers", 1)) > 1 and n_spk < int(cfg["num_speakers"]):
+        raise ValueError(f"config says num_speakers = {cfg['num_speakers']} but the model embeds {n_spk} speaker(s)")
     os.makedirs(out_dir, exist_ok=True)
     base = os.path.basename(config_path)
     stem = base[:-len(".onnx.json")] if base.endswith(".onnx.json") else os.path.splitext(base)[0]

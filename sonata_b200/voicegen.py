@@ -136,6 +136,27 @@ def tensor_specs(a: dict) -> "OrderedDict[str, tuple]":
     return s
 
 
+GIN_CHANNELS = 512      # Piper multi-speaker voices: gin_channels of SynthesizerTrn
+
+
+def speaker_specs(a: dict, n_speakers: int) -> "OrderedDict[str, tuple]":
+    """Extra tensors of a multi-speaker voice (`n_speakers > 1`, piper_train SynthesizerTrn): the speaker embedding and
+    the 1x1 conditioning convs applied to g = emb_g(sid): duration predictor (`dp.cond`), every coupling layer's
+    WaveNet (`enc.cond_layer`, all layers stacked: 2*hidden*n_layers rows) and the HiFi-GAN input (`dec.cond`)."""
+    H, G = a["hidden"], GIN_CHANNELS
+    s: "OrderedDict[str, tuple]" = OrderedDict()
+    s["emb_g.weight"] = ((n_speakers, G), "embg")
+    s["dp.cond.weight"] = ((H, G, 1), "wc")
+    s["dp.cond.bias"] = ((H,), "b")
+    for f in range(a["flow_n"]):
+        p = f"flow.flows.{2 * f}.enc.cond_layer."
+        s[p + "weight"] = ((2 * H * a["wn_layers"], G, 1), "wc")
+        s[p + "bias"] = ((2 * H * a["wn_layers"],), "b")
+    s["dec.cond.weight"] = ((a["up_init"], G, 1), "wc")
+    s["dec.cond.bias"] = ((a["up_init"],), "b")
+    return s
+
+
 def _rng(seed: int, name: str) -> np.random.Generator:
     return np.random.Generator(np.random.PCG64([seed, zlib.crc32(name.encode("utf-8"))]))
 
@@ -162,6 +183,10 @@ def base_tensor(seed: int, name: str, shape, kind: str) -> np.ndarray:
         v = n / np.sqrt(shape[2])
     elif kind == "ea":
         v = 0.1 * n
+    elif kind == "embg":
+        v = n
+    elif kind == "wc":      # conditioning conv: shifts of ~0.4 standard deviations per speaker
+        v = 0.4 * n / np.sqrt(shape[1])
     else:
         raise ValueError(kind)
     return v.astype(np.float32)
@@ -188,12 +213,15 @@ def load_gains(quality: str) -> dict:
         return json.load(f)
 
 
-def make_tensors(quality: str, seed: int = 1234, gains: dict | None = None):
+def make_tensors(quality: str, seed: int = 1234, gains: dict | None = None, n_speakers: int = 1):
     a = ARCH[quality]
     if gains is None:
         gains = load_gains(quality)
     out = hp_tensors(a)
-    for name, (shape, kind) in tensor_specs(a).items():
+    specs = tensor_specs(a)
+    if n_speakers > 1:
+        specs.update(speaker_specs(a, n_speakers))
+    for name, (shape, kind) in specs.items():
         t = base_tensor(seed, name, shape, kind)
         g = gains.get(name)
         if g is not None:
@@ -215,7 +243,7 @@ _SYMBOLS = (
 )
 
 
-def make_config(quality: str, num_symbols: int = 256, streaming: bool = False) -> dict:
+def make_config(quality: str, num_symbols: int = 256, streaming: bool = False, n_speakers: int = 1) -> dict:
     """A Piper-style ``*.onnx.json`` (schema: ``piper/src/lib.rs:112-158``)."""
     a = ARCH[quality]
     idmap = {"_": [0], "^": [1], "$": [2]}
@@ -235,8 +263,8 @@ def make_config(quality: str, num_symbols: int = 256, streaming: bool = False) -
                      "name_native": "English", "name_english": "English"},
         "inference": {"noise_scale": 0.667, "length_scale": 1.0, "noise_w": 0.8},
         "num_symbols": num_symbols,
-        "num_speakers": 1,
-        "speaker_id_map": {},
+        "num_speakers": n_speakers,
+        "speaker_id_map": {f"speaker_{i}": i for i in range(n_speakers)} if n_speakers > 1 else {},
         "streaming": streaming,
         "phoneme_map": {},
         "phoneme_id_map": idmap,
@@ -244,22 +272,22 @@ def make_config(quality: str, num_symbols: int = 256, streaming: bool = False) -
 
 
 def write_voice(dirpath: str, quality: str, seed: int = 1234, name: str | None = None,
-                streaming: bool = False) -> str:
+                streaming: bool = False, n_speakers: int = 1) -> str:
     """Write ``<dir>/<name>.onnx.json`` + ``<dir>/<name>.svw``; returns the config path.
 
     The weight file sits where the reference expects ``<name>.onnx`` (config path minus
     ``.json``, ``piper/src/lib.rs:98-108``) with the extension swapped to ``.svw``.
     """
     os.makedirs(dirpath, exist_ok=True)
-    name = name or f"synthetic-{quality}"
+    name = name or (f"synthetic-{quality}" if n_speakers <= 1 else f"synthetic-{quality}-spk{n_speakers}")
     cfg_path = os.path.join(dirpath, name + ".onnx.json")
     svw_path = os.path.join(dirpath, name + ".svw")
     if not (os.path.exists(cfg_path) and os.path.exists(svw_path)):
         tmp = svw_path + f".tmp{os.getpid()}"
-        write_svw(tmp, make_tensors(quality, seed))
+        write_svw(tmp, make_tensors(quality, seed, n_speakers=n_speakers))
         os.replace(tmp, svw_path)
         with open(cfg_path + f".tmp{os.getpid()}", "w", encoding="utf-8") as f:
-            json.dump(make_config(quality, streaming=streaming), f, ensure_ascii=False)
+            json.dump(make_config(quality, streaming=streaming, n_speakers=n_speakers), f, ensure_ascii=False)
         os.replace(cfg_path + f".tmp{os.getpid()}", cfg_path)
     return cfg_path
 

@@ -17,16 +17,17 @@ from sonata_b200.job import SynthesisJob  # noqa: E402
 from sonata_b200.piper import PiperSynthesisConfig  # noqa: E402
 
 
-def stage_report(quality="medium", n_list=(16,), noise=False, backend=0, seed=1234, verbose=True, utts=None):
+def stage_report(quality="medium", n_list=(16,), noise=False, backend=0, seed=1234, verbose=True, utts=None,
+                 n_speakers=1, sid=None):
     """utts: utterance seeds (default 0, 1, ...: the index in n_list); tests/screen_margin.py picks seeds whose
     durations are well clear of the ceil() cliff for the full-size cases."""
-    cfg_path = voicegen.write_voice(voicegen.default_voice_dir(), quality, seed)
-    W = vo.to_torch(voicegen.make_tensors(quality, seed))
+    cfg_path = voicegen.write_voice(voicegen.default_voice_dir(), quality, seed, n_speakers=n_speakers)
+    W = vo.to_torch(voicegen.make_tensors(quality, seed, n_speakers=n_speakers))
     a = vo.arch_of(W)
     model = sonata_b200.from_config_path(cfg_path)
     model.set_backend(backend)
     scales = [0.667, 1.0, 0.8] if noise else [0.0, 1.0, 0.0]
-    model.set_fallback_synthesis_config(PiperSynthesisConfig(None, scales[0], scales[1], scales[2]))
+    model.set_fallback_synthesis_config(PiperSynthesisConfig(sid, scales[0], scales[1], scales[2]))
     utts = list(range(len(n_list))) if utts is None else list(utts)
     batches = [vo.synthetic_ids(n, utt=u) for u, n in zip(utts, n_list)]
     g = torch.Generator().manual_seed(99)
@@ -38,9 +39,9 @@ def stage_report(quality="medium", n_list=(16,), noise=False, backend=0, seed=12
         ez = None
         if noise:
             st0 = {}
-            vo.encode(W, ids, scales, eps_w=ew, eps_z=None, stages=st0)
+            vo.encode(W, ids, scales, eps_w=ew, eps_z=None, stages=st0, sid=sid)
             ez = torch.randn(1, a["inter"], st0["y_len"], generator=g)
-        wav = vo.infer(W, ids, scales, eps_w=ew, eps_z=ez, stages=st)
+        wav = vo.infer(W, ids, scales, eps_w=ew, eps_z=ez, stages=st, sid=sid)
         refs.append(st)
         eps_w.append(None if ew is None else ew[0].T.contiguous().numpy())
         eps_z.append(None if ez is None else ez[0].T.contiguous().numpy())

@@ -124,6 +124,35 @@ def test_baseline_sizes_against_oracle(cfg, backend):
         assert u["logw_median_err"] < TOL_LOGW_MEDIAN, (cfg, seed, u["logw_median_err"])
 
 
+@pytest.mark.parametrize("backend", [1, 0], ids=["tcgen05", "fp32simt"])
+def test_multi_speaker_voice_against_oracle(backend, voice_paths):
+    """a multi-speaker voice (`emb_g`, `dp.cond`, the WaveNets' `cond_layer`, `dec.cond`) -- the graph
+    the reference feeds the `sid` tensor to whenever num_speakers > 1 (piper/src/lib.rs:353-358).  Every stage against
+    the oracle for two speakers, and the speakers must differ."""
+    from stage_report import stage_report
+    waves = {}
+    for sid in (0, 3):
+        rep = stage_report("medium", (21, 40), False, backend=backend, verbose=False, n_speakers=4, sid=sid)
+        for u in rep["utts"]:
+            assert u["durations_exact"] and u["y_len_ref"] == u["y_len_got"], (sid, u)
+            for name, err, ref_max in u["stages"]:
+                assert err != "SHAPE" and err < _stage_tol(name), (sid, name, err)
+        waves[sid] = [u["y_len_got"] for u in rep["utts"]]
+    cfg = voicegen.write_voice(voicegen.default_voice_dir(), "medium", n_speakers=4)
+    m = sonata_b200.from_config_path(cfg, device=0)
+    assert m.get_speakers() == {i: f"speaker_{i}" for i in range(4)} and m.speaker_name_to_id("speaker_2") == 2
+    ids = workload.synthetic_ids(30, utt=9)
+    outs = []
+    for sid in (None, 0, 2):                                   # speaker: None -> sid 0 (`unwrap_or(0)`)
+        m.set_fallback_synthesis_config(PiperSynthesisConfig(sid, 0.0, 1.0, 0.0))
+        outs.append(m.infer_with_values(ids).samples.as_slice().copy())
+    assert np.array_equal(outs[0], outs[1])
+    assert outs[2].shape != outs[1].shape or float(np.abs(outs[2] - outs[1]).max()) > 1e-2
+    with pytest.raises(sonata_b200.OperationError):
+        m.set_fallback_synthesis_config(PiperSynthesisConfig(9, 0.0, 1.0, 0.0))     # piper/src/lib.rs:215-231
+    m.close()
+
+
 def test_unscreened_duration_flips_are_cliff_cases():
     """Companion of the screened test: 8 x 256-phoneme utterances with ARBITRARY seeds.  A frame count may differ
     from the oracle's only where the oracle's own duration sits on the ceil() cliff (margin < 1e-3, where fp32

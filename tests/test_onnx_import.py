@@ -49,14 +49,14 @@ def _model(tensors) -> bytes:
     return _varint((1 << 3) | 0) + _varint(8) + _ld(2, b"pytorch") + _ld(7, graph)   # ir_version, producer, graph
 
 
-def _write_voice(tmp_path, quality, decompose=True, drop=None, extra=None):
-    tensors = voicegen.make_tensors(quality, 77)
+def _write_voice(tmp_path, quality, decompose=True, drop=None, extra=None, n_speakers=1):
+    tensors = voicegen.make_tensors(quality, 77, n_speakers=n_speakers)
     blobs = []
     for i, (name, arr) in enumerate(tensors.items()):
         if (drop and name == drop) or name.startswith("hp."):
             continue
         mode = ("raw", "float_data", "packed_dims")[i % 3]
-        if decompose and ".enc.in_layers." in name and name.endswith(".weight"):
+        if decompose and (".enc.in_layers." in name or ".enc.cond_layer." in name) and name.endswith(".weight"):
             # weight_norm(dim=0): g = ||w|| per output channel, v = any rescaling of w
             w = arr.astype(np.float64)
             g = np.sqrt((w * w).sum(axis=(1, 2), keepdims=True))
@@ -75,7 +75,7 @@ def _write_voice(tmp_path, quality, decompose=True, drop=None, extra=None):
     onnx = tmp_path / f"voice-{quality}.onnx"
     onnx.write_bytes(_model(blobs))
     cfg = tmp_path / f"voice-{quality}.onnx.json"
-    cfg.write_text(json.dumps(voicegen.make_config(quality)))
+    cfg.write_text(json.dumps(voicegen.make_config(quality, n_speakers=n_speakers)))
     return str(onnx), str(cfg), tensors
 
 
@@ -114,10 +114,20 @@ def test_reports_missing_and_anonymous(tmp_path):
     assert "dec.ups.1.weight" in str(e.value) and "anonymous" in str(e.value)
 
 
-def test_rejects_multi_speaker_and_garbage(tmp_path):
-    onnx, cfg, _ = _write_voice(tmp_path, "medium", decompose=False, extra={"emb_g.weight": np.zeros((4, 512), np.float32)})
-    with pytest.raises(ValueError, match="multi-speaker"):
-        onnx_import.import_voice(onnx, cfg, str(tmp_path / "out"))
+def test_multi_speaker_import_and_garbage(tmp_path):
+    """multi-speaker voices: `emb_g` + the conditioning convs (the weight-normed `cond_layer` folded like the in_layers)"""
+    onnx, cfg, ref = _write_voice(tmp_path, "medium", n_speakers=3)
+    out_cfg = onnx_import.import_voice(onnx, cfg, str(tmp_path / "out"))
+    got = read_svw(out_cfg[:-len(".onnx.json")] + ".svw")
+    spk = voicegen.speaker_specs(voicegen.ARCH["medium"], 3)
+    assert all(k in got for k in spk) and got["emb_g.weight"].shape == (3, 512)
+    for name in spk:
+        tol = 2e-6 if ".cond_layer.weight" in name else 0.0
+        assert np.abs(got[name] - ref[name]).max() <= tol * max(1.0, float(np.abs(ref[name]).max())), name
+    # an embedding without its conditioning layers is reported, not half-loaded
+    onnx2, cfg2, _ = _write_voice(tmp_path, "medium", decompose=False, extra={"emb_g.weight": np.zeros((4, 512), np.float32)})
+    with pytest.raises(ValueError, match="dp.cond.weight"):
+        onnx_import.import_voice(onnx2, cfg2, str(tmp_path / "out2"))
     bad = tmp_path / "bad.onnx"
     bad.write_bytes(_ld(2, b"not a model"))
     with pytest.raises(ValueError, match="GraphProto"):
