@@ -389,7 +389,7 @@ int32_t sb200_debug_conv(int32_t device, int32_t backend, const float* x, int32_
         SB_CUDA(cudaMalloc(&dend, 4)); SB_CUDA(cudaMemcpy(dend, &valid_rows, 4, cudaMemcpyHostToDevice));
         ConvArgs p{};
         p.x = dx; p.ldx = cin; p.rows_in = R; p.cin = cin; p.in_slope = in_slope;
-        p.w = cw.w; p.bias = cw.bias; p.ldw = cw.ldw; p.cout = cw.cout; p.wtc = cw.wtc; p.tc_nt = cw.tc_nt; p.wts = cw.wts; p.wcat = cw.wcat;
+        p.w = cw.w; p.bias = cw.bias; p.ldw = cw.ldw; p.cout = cw.cout; p.wtc = cw.wtc; p.tc_nt = cw.tc_nt; p.wcat = cw.wcat;
         p.ntaps = cw.ntaps; memcpy(p.tap_off, cw.tap_off, sizeof(p.tap_off)); p.min_off = cw.min_off; p.span = cw.span;
         p.rows_q = R; p.orow_mul = 1; p.orow_add = 0;
         p.map = RowMap{dend, R, 1, R};

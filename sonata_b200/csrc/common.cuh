@@ -42,7 +42,6 @@ struct ConvArgs {
     const float* x; int ldx; int rows_in; int cin; float in_slope;
     const float* w; const float* bias; int ldw; int cout;
     const float* wtc; int tc_nt;                                  // tcgen05 weight images (conv_tc.cu) or null
-    const float* wts;                                             // tap-stacked weight images (conv_ts.cu) or null
     const float* wcat;                                            // hi/lo-stacked tap-pair images (conv_tc.cu cat mode) or null
     const float* wtf;                                             // tf32 hi/lo images (conv_tf.cu) or null
     int ntaps; int tap_off[SB_MAX_TAPS]; int min_off; int span;   // span = max_off - min_off
@@ -111,10 +110,6 @@ void conv_tf_build_weights(const float* wt, int ldw, int cin, int cout, int ntap
 bool gemm_tf_supported(const TfGemm& g);
 void launch_gemm_tf(const TfGemm& g, cudaStream_t st);
 void throw_launch_error(const char* what);
-bool conv_ts_supported(const ConvArgs& a);
-void launch_conv_ts(const ConvArgs& a, cudaStream_t st);
-size_t conv_ts_weight_floats(int ntaps);
-void conv_ts_build_weights(const float* wt, int ldw, int ntaps, float* out);
       // column tile the SIMT kernel will use for this cout (for weight padding)
 
 struct SegInfo { int off; int len; };   // rows

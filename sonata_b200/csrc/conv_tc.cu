@@ -33,7 +33,6 @@
 //     loads into SWIZZLE_128B staging tiles, the result is written over the residual tile in place and
 //     leaves with one TMA tensor store per tile, all issued by an agent lane of the idle weight warp -- the
 //     SM's load/store path sees no global traffic at all (ncu: that path, not HBM, bounded these layers);
-//   * MODE 1 (opt-in experiment): four taps x 32 channels stacked along N, see plan_stk().
 // Persistent CTAs (one per SM) walk tiles blockIdx.x, +gridDim.x, ...; mbarrier pipelines (activation
 // ring, weight ring, 4-stage TMEM accumulator ring, MODE 2 staging) run across tile boundaries.
 // Warps: w0/w1 MMA issuers on alternating tiles (w0 also allocates TMEM), w2/w3 weight producers and
@@ -68,10 +67,6 @@ struct TcLaunch {
     int bulk_in;     // input rows are contiguous 128-B rows (ldx == 32): a window is ONE block -> one TMA bulk copy
     int tma_in;      // the window of a K-block arrives by ONE TMA tensor load (box 32 channels x win rows; rows outside
                      // the array are zero-filled by the engine): no LDGSTS traffic through the LSU / L1TEX pipe
-    // "stacked" mode (STK): the N = 128 columns of a tile are 128/cout TAPS x cout channels (see the epilogue)
-    int tq;          // output rows per tile (128 normally; 128 - (slots-1)*dil when stacked)
-    int slots;       // taps stacked along N
-    int dil;         // tap spacing in rows
     int depth;       // window loads in flight per pipeline (< na: see plan())
     int v8;          // every epilogue operand is 32-byte aligned: 256-bit global accesses
     int tma_st;      // MODE 2: output tile leaves through a TMA tensor store
@@ -93,16 +88,13 @@ constexpr int TC2_THREADS = 640;        // w0/w1 MMA issuers, w2/w3 weight produ
                                         // w12-15 / w16-19 epilogue groups (pipeline 0 / 1)
 constexpr int TC_MAX_ASTAGES = 4;       // per pipeline
 constexpr int TC_MAX_WRING = 44;        // barrier slots for the resident weight set (or 2 x ring)
-constexpr int TC_EX_STRIDE = 80;        // stacked mode: bytes per row of the slot-exchange buffer (16 floats + 16 B pad:
-                                        // 128-bit accesses of 8 consecutive rows hit 8 different bank groups)
-constexpr int TC_EX_BYTES = 128 * TC_EX_STRIDE;
 constexpr int TC_OUT_BYTES = 128 * 128;  // MODE 2: one staged output tile (128 rows x 32 fp32), two per pipeline
 
 // The CTA runs TWO independent half-pipelines (p = 0 / 1 own tiles tl = p, p+2, ...): one thread can issue an
 // M=128 MMA only every ~83 cycles whatever N is, while two issuing warps double the aggregate rate
 // (tools/micro/mma_bench.cu: N=32 385 -> 774 MAC/clk/SM, N=128 1572 -> 2046 = peak).  Each pipeline has its
 // own activation ring, weight ring and accumulator pair, so no mbarrier can be lapped by the other pipeline.
-// MODE 0: plain mapping (one tap per MMA, N = nt).  MODE 1: stacked taps (experimental, see plan_stk()).
+// MODE 0: plain mapping (one tap per MMA, N = nt).
 // MODE 2: plain mapping for 32-channel outputs with the tile written by ONE TMA tensor store from a swizzled
 // shared-memory staging tile (see the epilogue).
 template <int MODE>
@@ -110,7 +102,6 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                                                                   const __grid_constant__ CUtensorMap tm_out,
                                                                   const __grid_constant__ CUtensorMap tm_res,
                                                                   const __grid_constant__ CUtensorMap tm_x) {
-    constexpr bool STK = MODE == 1;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t a_buf = (uint32_t)L.win * 128u;              // one [hi|lo] window image
@@ -119,8 +110,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
     const int wslots = L.resident ? L.ws : 2 * L.ws;
     uint8_t* A0 = smem;                                         // [2][na] stages
     uint8_t* W0 = A0 + (size_t)2 * L.na * a_buf;                // resident: [ws]; ring: [2][ws]
-    uint8_t* EX = W0 + (size_t)wslots * w_stage;                // stacked mode: [2 pipelines] slot-exchange buffers
-    uint64_t* bars = reinterpret_cast<uint64_t*>(EX + (STK ? 2 * TC_EX_BYTES : MODE == 2 ? 4 * TC_OUT_BYTES : 0));
+    uint8_t* EX = W0 + (size_t)wslots * w_stage;                // MODE 2: [2 pipelines][2] staging tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(EX + (MODE == 2 ? 4 * TC_OUT_BYTES : 0));
     uint64_t* w_full = bars;                               // [TC_MAX_WRING]
     uint64_t* w_empty = w_full + TC_MAX_WRING;             // [TC_MAX_WRING]
     uint64_t* a_full = w_empty + TC_MAX_WRING;             // [2][TC_MAX_ASTAGES]
@@ -303,7 +294,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
         auto issue_stage = [&](int j) {
             const int lt = j / nkb, kb = j - lt * nkb;
             const int tg = (int)blockIdx.x + (p + 2 * lt) * (int)gridDim.x;
-            const int rbase = (tg / L.ntiles_n) * L.tq + a.min_off;
+            const int rbase = (tg / L.ntiles_n) * 128 + a.min_off;
             const int as = j % L.na;
             mbar_wait(smem_u32(&a_empty[p * TC_MAX_ASTAGES + as]), (uint32_t)(((j / L.na) & 1) ^ 1));
             if (p == 0 && gt == 0 && kb == 0) TC_TRACE(a, lt, 0);
@@ -349,7 +340,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
             {
                 const int lt_ = j / nkb;
                 const int tg_ = (int)blockIdx.x + (p + 2 * lt_) * (int)gridDim.x;
-                const int rb_ = (tg_ / L.ntiles_n) * L.tq + a.min_off;
+                const int rb_ = (tg_ / L.ntiles_n) * 128 + a.min_off;
                 if (L.tma_in || (L.bulk_in && rb_ >= 0 && rb_ + L.win <= a.rows_in)) {
                     const int as_ = j % L.na;
                     mbar_wait(smem_u32(&raw_full[p * TC_MAX_ASTAGES + as_]), (rawpar >> as_) & 1u);
@@ -408,106 +399,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
         const int p = (warp - TC_EPI0) >> 2;
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
-        if constexpr (STK) {
-            // ---- stacked mode: column n = s*cout + co of the accumulator is tap slot s of channel co, evaluated
-            // at window row `row`; it belongs to output row (row - s*dil).  Slot 0 is this thread's own row; the
-            // other slots come from the threads `s*dil` rows further down, through a small shared-memory exchange
-            // (row-per-thread stays: float4 global accesses, ~4x fewer instructions than a transposed epilogue).
-            const int cw = a.cout, npc = cw >> 4;                      // 16-column pieces
-            const uint32_t ex = smem_u32(EX + (size_t)p * TC_EX_BYTES);
-            const uint32_t ex_w = ex + (uint32_t)row * TC_EX_STRIDE;
-            const int bar_id = 1 + p;
-            for (int tl = p, lt = 0; tl < my_tiles; tl += 2, lt++) {
-                const int tg = (int)blockIdx.x + tl * (int)gridDim.x;
-                const int q = tg * L.tq + row;
-                const int acc = p + 2 * (lt & 1);
-                const bool inrange = row < L.tq && q < a.rows_q;
-                const bool valid = inrange && row_valid(a.map, q);
-                const size_t orow = (size_t)q + a.orow_add;
-                float mc[16], mn[16];
-                auto pre = [&](int h, float* m) {                      // m = res*scale + prev for columns [16h, 16h+16)
-#pragma unroll
-                    for (int j = 0; j < 16; j++) m[j] = 0.f;
-                    if (a.res && valid) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 8) {
-                            float r[8];
-                            ldg256(a.res + orow * a.ldres + h * 16 + j, r);
-#pragma unroll
-                            for (int e = 0; e < 8; e++) m[j + e] = r[e] * a.scale;
-                        }
-                    }
-                    if (a.acc0 && valid) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 8) {
-                            float r[8];
-                            ldg256(a.y0 + orow * a.ldy0 + h * 16 + j, r);
-#pragma unroll
-                            for (int e = 0; e < 8; e++) m[j + e] += r[e];
-                        }
-                    }
-                };
-                pre(0, mc);
-                mbar_wait(smem_u32(&acc_full[acc]), (uint32_t)((lt >> 1) & 1));
-                tc_fence_after();
-                if (p == 0 && warp == TC_EPI0 && lane == 0) TC_TRACE(a, lt, 5);
-                const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * L.accw);
-                for (int h = 0; h < npc; h++) {
-                    if (h + 1 < npc) pre(h + 1, mn);
-                    float o[16];
-                    tmem_ld16(tcol + (uint32_t)(h * 16), o);
-                    for (int sl = 1; sl < L.slots; sl++) {
-                        float t[16];
-                        tmem_ld16(tcol + (uint32_t)(sl * cw + h * 16), t);
-                        if (h == npc - 1 && sl == L.slots - 1) {       // accumulator fully read: hand it back
-                            tc_fence_before();
-                            mbar_arrive(smem_u32(&acc_empty[acc]));
-                            if (p == 0 && warp == TC_EPI0 && lane == 0) TC_TRACE(a, lt, 6);
-                        }
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            uint4 u;
-                            u.x = __float_as_uint(t[j]); u.y = __float_as_uint(t[j + 1]);
-                            u.z = __float_as_uint(t[j + 2]); u.w = __float_as_uint(t[j + 3]);
-                            sts128u(ex_w + (uint32_t)j * 4u, u);
-                        }
-                        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-                        const int rsrc = row + sl * L.dil;             // rows >= 128 only feed rows >= tq (not stored)
-                        if (rsrc < 128) {
-                            const uint32_t ex_r = ex + (uint32_t)rsrc * TC_EX_STRIDE;
-#pragma unroll
-                            for (int j = 0; j < 16; j += 4) {
-                                const float4 x = lds128(ex_r + (uint32_t)j * 4u);
-                                o[j] += x.x; o[j + 1] += x.y; o[j + 2] += x.z; o[j + 3] += x.w;
-                            }
-                        }
-                        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-                    }
-                    if (L.slots == 1 && h == npc - 1) { tc_fence_before(); mbar_arrive(smem_u32(&acc_empty[acc])); }
-                    if (inrange && !(a.acc0 && !valid)) {              // accumulated buffers keep their gap zeros
-                        if (a.bias) {
-#pragma unroll
-                            for (int j = 0; j < 16; j += 4) {
-                                const float4 b = *reinterpret_cast<const float4*>(a.bias + h * 16 + j);
-                                o[j] += b.x; o[j + 1] += b.y; o[j + 2] += b.z; o[j + 3] += b.w;
-                            }
-                        }
-                        if (a.act == ACT_RELU) {
-#pragma unroll
-                            for (int j = 0; j < 16; j++) o[j] = fmaxf(o[j], 0.f);
-                        }
-#pragma unroll
-                        for (int j = 0; j < 16; j++) o[j] = valid ? fmaf(o[j], a.scale, mc[j]) : 0.f;
-                        float* dst = a.y0 + orow * a.ldy0 + h * 16;
-                        stg256(dst, o);
-                        stg256(dst + 8, o + 8);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 16; j++) mc[j] = mn[j];
-                }
-                if (p == 0 && warp == TC_EPI0 && lane == 0) TC_TRACE(a, lt, 7);
-            }
-        } else if constexpr (MODE == 2) {
+        if constexpr (MODE == 2) {
             // ---- 32-channel output, row-per-thread math, but every global operand of the epilogue moves through the
             // TMA engine: the residual and previous-value tiles arrive in SWIZZLE_128B staging tiles (16-byte chunk
             // c of row r at c ^ (r & 7): conflict-free 128-bit accesses for a row-per-thread owner), the result is
@@ -681,7 +573,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
             }
             if (p == 0 && warp == TC_EPI0 && lane == 0) TC_TRACE(a, lt, 7);
         }
-        }   // !STK
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -715,7 +607,6 @@ bool epi_v8_ok(const ConvArgs& a) {
 bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem) {
     if (!a.wtc || a.tc_nt <= 0 || a.tc_nt > 128) return false;
     L.nt = a.tc_nt;
-    L.tq = 128; L.slots = 1; L.dil = 1;
     L.v8 = epi_v8_ok(a) ? 1 : 0;
     L.tma_st = (L.v8 && a.cout == 32 && L.nt == 32 && a.act != ACT_GATE && !a.phase_cols && a.split >= a.cout && a.orow_mul == 1 &&
                 tensor_map_encoder() != nullptr && !getenv("SB200_TC_NOTMAST")) ? 1 : 0;
@@ -750,51 +641,6 @@ bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem) {
     { const char* e = getenv("SB200_TC_NA"); if (e) L.na = atoi(e); }     // tuning knob
     while (L.na > 2 && total() > budget) L.na--;
     while (!L.resident && L.ws > 2 && total() > budget) L.ws--;
-    if (total() > budget) return false;
-    L.depth = L.na - 1;
-    { const char* e = getenv("SB200_TC_DEPTH"); if (e && atoi(e) >= 1 && atoi(e) < L.na) L.depth = atoi(e); }
-    smem = total() + 2048;
-    return true;
-}
-
-// Stacked mode (32-channel layers with >= 3 uniformly spaced taps): the N = 128 columns of a tile hold FOUR
-// taps x 32 output channels, so a k-tap layer issues ceil(k/4) * 6 full-width MMAs per tile instead of k * 6
-// quarter-width ones.  `v` receives the arguments the kernel runs with: one "virtual tap" per group of four
-// taps (its window offset is the group's first tap), stacked weight images.
-// MEASURED (C2, mrf2): 14.2 ms vs 10.2 ms for the plain mapping -- 3.5x fewer MMAs did not help, the tensor
-// pipe sustains the same ~600 MAC/clk/SM either way: opt-in via SB200_STK, kept for round 2.
-bool plan_stk(const ConvArgs& a, ConvArgs& v, TcLaunch& L, size_t& smem) {
-    if (!a.wts || a.cin != 32 || a.cout != 32 || a.ntaps < 3 || a.ntaps > 16) return false;
-    if (a.orow_mul != 1 || a.phase_cols || a.act == ACT_GATE || a.split < a.cout) return false;
-    if (!getenv("SB200_STK") || !epi_v8_ok(a)) return false;
-    const int dil = a.tap_off[1] - a.tap_off[0];
-    if (dil < 1) return false;
-    for (int t = 0; t < a.ntaps; t++) if (a.tap_off[t] != a.min_off + t * dil) return false;
-    const int slots = 4, ng = (a.ntaps + slots - 1) / slots;
-    L.nt = 128; L.slots = slots; L.dil = dil; L.cat = 0; L.accw = 128; L.idesc2 = 0;
-    L.tq = 128 - (slots - 1) * dil;
-    if (L.tq < 32) return false;
-    v = a;
-    v.ntaps = ng;
-    for (int g = 0; g < ng; g++) v.tap_off[g] = a.min_off + g * slots * dil;
-    v.span = (ng - 1) * slots * dil;
-    v.wtc = a.wts; v.tc_nt = 128;
-    L.win = (128 + v.span + 7) & ~7;
-    if (L.win * 4 > TC_MAXCH * TC_GROUP) return false;
-    L.tmem_cols = 512;
-    L.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    L.ntiles_m = (a.rows_q + L.tq - 1) / L.tq;
-    L.ntiles_n = 1;
-    const size_t a_buf = (size_t)L.win * 128, w_stage = 128 * 128;
-    const size_t budget = 225 * 1024 - 2048;
-    const size_t bar_bytes = (2 * TC_MAX_WRING + 6 * TC_MAX_ASTAGES + 12) * 8 + 16;
-    L.bulk_in = (getenv("SB200_TC_NOBULKIN") == nullptr && a.ldx == 32) ? 1 : 0;
-    L.tma_in = 0;
-    L.resident = 1; L.ws = ng;
-    L.na = TC_MAX_ASTAGES;
-    { const char* e = getenv("SB200_TC_NA"); if (e) L.na = atoi(e); }
-    auto total = [&]() { return (size_t)2 * L.na * a_buf + (size_t)ng * w_stage + 2 * TC_EX_BYTES + bar_bytes; };
-    while (L.na > 2 && total() > budget) L.na--;
     if (total() > budget) return false;
     L.depth = L.na - 1;
     { const char* e = getenv("SB200_TC_DEPTH"); if (e && atoi(e) >= 1 && atoi(e) < L.na) L.depth = atoi(e); }
@@ -859,11 +705,9 @@ static int tc_num_sms() {
 }
 
 void launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
-    if (conv_ts_supported(a)) { launch_conv_ts(a, st); return; }      // experimental transposed kernel (opt-in)
     static PerDeviceOnce once;
     once.run([] {
         cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     TcLaunch L; size_t smem;
@@ -872,13 +716,6 @@ void launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     memset(&tm, 0, sizeof(tm));
     memset(&tmr, 0, sizeof(tmr));
     memset(&tmx, 0, sizeof(tmx));
-    if (plan_stk(a, v, L, smem)) {                                    // experimental: four taps per MMA (opt-in)
-        const int grid = L.ntiles_m < tc_num_sms() ? L.ntiles_m : tc_num_sms();
-        conv_tc_kernel<1><<<grid, TC2_THREADS, smem, st>>>(v, L, tm, tmr, tmx);
-        g_launch_count++;
-        check_launch("conv_tc_stk");
-        return;
-    }
     if (!plan(a, L, smem)) { launch_conv_simt(a, st); return; }
     const int tiles = L.ntiles_m * L.ntiles_n;
     const int grid = tiles < tc_num_sms() ? tiles : tc_num_sms();

@@ -23,8 +23,8 @@
 //   * weights: hi / lo images pre-split at voice-load time, one cp.async.bulk per (K-block, tap) stage.
 //   * epilogue: tcgen05.ld of each finished chunk -> running sums (96 registers per thread); after the last chunk
 //     bias / ReLU / residual / scale / accumulate and 256-bit row-per-thread stores.
-// Warps: w0/w1 MMA issuers (w0 allocates TMEM), w2 weight loader, w3 activation loader, w4-5 converters,
-// w6-9 / w10-13 epilogue groups of issuer 0 / 1.  Every mbarrier wait carries the watchdog of tc_common.cuh.
+// Warps: w0/w1 MMA issuers (w0 allocates TMEM), w2 weight loader, w3 activation loader, w4-7 converters,
+// w8-11 / w12-15 epilogue groups of issuer 0 / 1.  Every mbarrier wait carries the watchdog of tc_common.cuh.
 //
 // GM = 1 instantiation ("grouped GEMM", the two contractions of the relative-position attention): the B operand is
 // not a pre-split weight image but a second ACTIVATION matrix (K for Q.K^T, V^T for P.V), fetched by TMA tensor loads
@@ -42,7 +42,8 @@ using namespace tcx;
 
 constexpr int TF_WARP_WLOAD = 2, TF_WARP_ALOAD = 3, TF_WARP_CONV0 = 4;
 template <int GM> struct TfCfg {
-    static constexpr int NCONV = GM ? 128 : 64;                    // converter threads
+    static constexpr int NCONV = 128;                              // converter threads (64 could not keep up with two issuers on
+                                                                   // 1x1 layers: 2 x 128 rows per 12 MMAs; ncu: tensor pipe 17 %)
     static constexpr int WARP_EPI0 = TF_WARP_CONV0 + NCONV / 32;   // first epilogue warp
     static constexpr int THREADS = (WARP_EPI0 + 8) * 32;
 };
@@ -395,12 +396,18 @@ __global__ void __launch_bounds__(TfCfg<GM>::THREADS, 1) conv_tf_kernel(const Co
     }
 }
 
-int tf_nth_for(int cout) {
+// Column tile.  k-tap layers (ffn): 96 columns -- an activation stage feeds 3 x 12 MMAs, so two ring stages hide the
+// load + conversion latency (ncu: tensor pipe ~50 %).  1x1 layers: an activation stage feeds only 12 MMAs (~1000 cycles)
+// while a TMA load + conversion takes ~2000, so they want THREE stages per issuer, which only fits next to 64-column
+// weight stages (ncu with 96 columns / 2 stages: tensor pipe 12-20 %, 35-57 TFLOP/s against 150-160 for the k3 layers).
+int tf_nth_for(int cout, int ntaps) {
+    if (ntaps == 1 && cout % 64 == 0) return 64;
     if (cout % 96 == 0) return 96;
     if (cout % 64 == 0) return 64;
     if (cout % 32 == 0) return 32;
     return 0;
 }
+constexpr size_t TF_SMEM_BUDGET = 227 * 1024 - 1024;     // opt-in maximum minus the slack of the manual 1024-byte alignment
 
 bool plan(const ConvArgs& a, TfLaunch& L, size_t& smem) {
     if (!a.wtf || a.cin % 32 || a.cout % 32 || a.ntaps < 1 || a.ntaps > SB_MAX_TAPS) return false;
@@ -409,7 +416,7 @@ bool plan(const ConvArgs& a, TfLaunch& L, size_t& smem) {
     auto al32 = [](const void* p, int ld) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 31) == 0 && (ld & 7) == 0); };
     if (!al32(a.y0, a.ldy0) || !al32(a.res, a.ldres)) return false;
     if ((a.ldx & 3) || (reinterpret_cast<uintptr_t>(a.x) & 15)) return false;
-    L.nth = tf_nth_for(a.cout);
+    L.nth = tf_nth_for(a.cout, a.ntaps);
     if (!L.nth) return false;
     L.win = (128 + a.span + 7) & ~7;
     if (L.win > 256) return false;
@@ -423,15 +430,21 @@ bool plan(const ConvArgs& a, TfLaunch& L, size_t& smem) {
     L.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(L.nth >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const size_t a_img = (size_t)L.win * 128, w_stage = (size_t)L.nth * 256;
     const size_t bar_bytes = (3 * TF_NW_MAX + 6 * TF_NA_MAX + 8) * 8 + 16;
-    const size_t budget = 225 * 1024 - 2048;
+    const size_t budget = TF_SMEM_BUDGET;
     L.na = 2; L.nw = 2;
     auto total = [&]() { return (size_t)2 * L.na * 2 * a_img + (size_t)L.nw * w_stage + bar_bytes; };
     if (total() > budget) return false;
-    // weight stages turn over ntaps times faster than activation stages: deepen the weight ring first
-    while (L.nw < TF_NW_MAX && L.nw < 2 * a.ntaps + 2) { L.nw++; if (total() > budget) { L.nw--; break; } }
-    while (L.na < TF_NA_MAX) { L.na++; if (total() > budget) { L.na--; break; } }
+    if (a.ntaps == 1) {
+        // 1x1: activation stages first (see tf_nth_for), then whatever is left for the weight ring
+        while (L.na < 3) { L.na++; if (total() > budget) { L.na--; break; } }
+        while (L.nw < 4) { L.nw++; if (total() > budget) { L.nw--; break; } }
+    } else {
+        // weight stages turn over ntaps times faster than activation stages: deepen the weight ring first
+        while (L.nw < TF_NW_MAX && L.nw < 2 * a.ntaps + 2) { L.nw++; if (total() > budget) { L.nw--; break; } }
+        while (L.na < TF_NA_MAX) { L.na++; if (total() > budget) { L.na--; break; } }
+    }
     { const char* e = getenv("SB200_TF_NW"); if (e && atoi(e) >= 2 && atoi(e) <= TF_NW_MAX) { const int o = L.nw; L.nw = atoi(e); if (total() > budget) L.nw = o; } }
-    smem = total() + 2048;
+    smem = total() + 1024;
     return true;
 }
 
@@ -499,17 +512,17 @@ void launch_gemm_tf(const TfGemm& g, cudaStream_t st) {
     L.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(L.nth >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const size_t a_img = 128 * 128, w_stage = (size_t)L.nth * 256;
     const size_t bar_bytes = (3 * TF_NW_MAX + 6 * TF_NA_MAX + 8) * 8 + 16;
-    const size_t budget = 225 * 1024 - 2048;
+    const size_t budget = TF_SMEM_BUDGET;
     L.na = 2; L.nw = 2;
     auto total = [&]() { return (size_t)2 * L.na * 2 * a_img + (size_t)L.nw * w_stage + bar_bytes; };
+    while (L.na < 3) { L.na++; if (total() > budget) { L.na--; break; } }     // one K-block = 12 MMAs: activation stages first
     while (L.nw < 4) { L.nw++; if (total() > budget) { L.nw--; break; } }
-    while (L.na < TF_NA_MAX) { L.na++; if (total() > budget) { L.na--; break; } }
     CUtensorMap tma, tmb;
     if (!tensor_map_2d(&tma, g.a, (unsigned long long)g.a_cols, (unsigned long long)g.a_rows, (unsigned long long)g.lda, 32, 128, true) ||
         !tensor_map_2d(&tmb, g.b, (unsigned long long)g.b_cols, (unsigned long long)g.b_rows, (unsigned long long)g.ldb, 32, (unsigned)g.nth, true))
         throw_launch_error("gemm_tf: tensor map encoding failed");
     const int grid = g.ntiles < tf_num_sms() ? g.ntiles : tf_num_sms();
-    conv_tf_kernel<1><<<grid, TfCfg<1>::THREADS, total() + 2048, st>>>(a, L, tma, tmb, g.tiles);
+    conv_tf_kernel<1><<<grid, TfCfg<1>::THREADS, total() + 1024, st>>>(a, L, tma, tmb, g.tiles);
     g_launch_count++;
     check_launch("gemm_tf");
 }
@@ -518,13 +531,13 @@ void launch_gemm_tf(const TfGemm& g, cudaStream_t st) {
 // lo image; row n = 32 channels fp32 of output column n, K-major SWIZZLE_128B (16-byte chunk c at c ^ (n & 7)).
 // hi = tf32_rn(w), lo = tf32_rn(w - hi).  Sizes in floats.
 size_t conv_tf_weight_floats(int cin, int cout, int ntaps) {
-    const int nth = tf_nth_for(cout);
+    const int nth = tf_nth_for(cout, ntaps);
     if (!nth || cin % 32) return 0;
     return (size_t)(cout / nth) * (cin / 32) * ntaps * nth * 64;
 }
 
 void conv_tf_build_weights(const float* wt /*[ntaps][cin][ldw]*/, int ldw, int cin, int cout, int ntaps, float* out) {
-    const int nth = tf_nth_for(cout);
+    const int nth = tf_nth_for(cout, ntaps);
     const int ntiles = cout / nth, nkb = cin / 32;
     uint32_t* o32 = reinterpret_cast<uint32_t*>(out);
     size_t o = 0;

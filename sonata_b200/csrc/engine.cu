@@ -122,10 +122,10 @@ Job* create_job(Voice* v, const long long* ids, const size_t* offs, size_t B, co
         // A = Q rows, B = K rows of the fused q/k/v activation [RX][3H]; O = P.V: A = P rows of S viewed as
         // [heads*RX][Tp], B = V^T [H][RX] (the q/k/v projection stores V transposed).
         const int H = v->a.hidden, heads = v->a.heads, D = H / heads;
-        j->att_tp = round_up(std::max(j->max_tx, 1), 96);
+        j->att_tp = round_up(std::max(j->max_tx, 1), 64);      // key tile of the Q.K^T GEMM (64: see conv_tf.cu tf_nth_for)
         for (size_t b = 0; b < B; b++) {
             const int off = j->xsegs[b].off, T = j->xsegs[b].len;
-            const int nmp = (T + 255) / 256, nnt = (T + 95) / 96;
+            const int nmp = (T + 255) / 256, nnt = (T + 63) / 64;
             for (int h = 0; h < heads; h++)
                 for (int mp = 0; mp < nmp; mp++) {
                     TfTile t{};
@@ -133,14 +133,14 @@ Job* create_job(Voice* v, const long long* ids, const size_t* offs, size_t B, co
                         const int r0 = (mp * 2 + m) * 128;
                         t.rows_valid[m] = std::max(0, std::min(128, T - r0));
                     }
-                    // Q.K^T: one tile per 96-key block
+                    // Q.K^T: one tile per 64-key block
                     for (int nt = 0; nt < nnt; nt++) {
                         TfTile s = t;
                         for (int m = 0; m < 2; m++) {
                             s.a_row0[m] = off + (mp * 2 + m) * 128;
-                            s.out_off[m] = ((long long)h * j->RX + s.a_row0[m]) * j->att_tp + (long long)nt * 96;
+                            s.out_off[m] = ((long long)h * j->RX + s.a_row0[m]) * j->att_tp + (long long)nt * 64;
                         }
-                        s.a_col0 = h * D; s.b_row0 = off + nt * 96; s.b_col0 = H + h * D; s.nkb = D / 32;
+                        s.a_col0 = h * D; s.b_row0 = off + nt * 64; s.b_col0 = H + h * D; s.nkb = D / 32;
                         j->tiles_s.push_back(s);
                     }
                     // P.V: K runs over the utterance's keys in blocks of 32 (the softmax zero-fills up to the block end)
@@ -196,7 +196,7 @@ struct Runner {
     void conv(const ConvW& w, const float* x, int ldx, const Level& lin, const Opt& o) {
         ConvArgs p{};
         p.x = x; p.ldx = ldx; p.rows_in = lin.map.rows; p.cin = w.cin; p.in_slope = o.in_slope;
-        p.w = w.w; p.bias = bias_of(w); p.ldw = w.ldw; p.cout = w.cout; p.wtc = w.wtc; p.tc_nt = w.tc_nt; p.wts = w.wts; p.wcat = w.wcat; p.wtf = w.wtf;
+        p.w = w.w; p.bias = bias_of(w); p.ldw = w.ldw; p.cout = w.cout; p.wtc = w.wtc; p.tc_nt = w.tc_nt; p.wcat = w.wcat; p.wtf = w.wtf;
         p.ntaps = w.ntaps; memcpy(p.tap_off, w.tap_off, sizeof(p.tap_off)); p.min_off = w.min_off; p.span = w.span;
         p.rows_q = lin.map.rows; p.orow_mul = o.orow_mul; p.orow_add = o.orow_add;
         p.map = lin.map;
@@ -471,7 +471,7 @@ void Job::run(float* d_out, size_t d_out_cap) {
         att_orel = C.dev.get<float>((size_t)RX * H);
         gs.a = qkv; gs.a_rows = RX; gs.a_cols = 3 * H; gs.lda = 3 * H;
         gs.b = qkv; gs.b_rows = RX; gs.b_cols = 3 * H; gs.ldb = 3 * H;
-        gs.nth = 96; gs.y = att_s; gs.ldy = att_tp; gs.res = nullptr; gs.scale = 1.0f / sqrtf((float)(H / a.heads));
+        gs.nth = 64; gs.y = att_s; gs.ldy = att_tp; gs.res = nullptr; gs.scale = 1.0f / sqrtf((float)(H / a.heads));
         gs.tiles = d_tiles_s; gs.ntiles = (int)tiles_s.size();
         go.a = att_s; go.a_rows = a.heads * RX; go.a_cols = att_tp; go.lda = att_tp;
         go.b = att_vt; go.b_rows = H; go.b_cols = RX; go.ldb = RX;

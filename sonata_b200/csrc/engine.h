@@ -49,7 +49,6 @@ struct ConvW {
     float* w = nullptr;
     float* bias = nullptr;
     float* wtc = nullptr; int tc_nt = 0;     // tcgen05 hi/lo swizzled weight images
-    float* wts = nullptr;                    // tap-stacked images for the 32-channel layers (conv_ts.cu)
     float* wcat = nullptr;                   // hi/lo-stacked tap-pair images (conv_tc.cu cat mode), column tiles <= 64
     float* wtf = nullptr;                    // tf32 hi/lo images (conv_tf.cu): text-encoder / duration-predictor layers
     int cin = 0, cout = 0, ldw = 0, ntaps = 0;

@@ -1,4 +1,4 @@
-// PTX helpers shared by the tcgen05 kernels (conv_tc.cu, conv_ts.cu): mbarrier, cp.async.bulk, tcgen05
+// PTX helpers shared by the tcgen05 kernels (conv_tc.cu, conv_tf.cu): mbarrier, cp.async.bulk, tcgen05
 // fences / commit / MMA / TMEM loads, shared-space vector accesses, the bf16 hi/lo splitter.
 #pragma once
 #include "common.cuh"

@@ -101,11 +101,6 @@ void add_tc_images(Uploader& U, ConvW& c, const std::vector<float>& wt) {
         conv_tc_build_weights_cat(wt.data(), c.ldw, c.cin, c.cout, c.ntaps, nt, cat.data());
         c.wcat = U.up(cat);
     }
-    if (c.cin == 32 && c.cout == 32 && c.ntaps >= 3 && c.ntaps <= 16) {   // stacked-tap images (conv_tc.cu STK mode)
-        std::vector<float> ts(conv_ts_weight_floats(c.ntaps));
-        conv_ts_build_weights(wt.data(), c.ldw, c.ntaps, ts.data());
-        c.wts = U.up(ts);
-    }
 }
 
 // Conv1d weight [cout][cin][k] (+bias) -> ConvW with taps (t - (k-1)/2) * dil.

@@ -200,10 +200,10 @@ def test_conv_tf_kernel_fp32_class_accuracy(lib_built):
         assert err < TF_TOL, (c, err)
 
 
-@pytest.mark.parametrize("knob", ["SB200_TS", "SB200_STK", "SB200_TC_NOTMAST", "SB200_TC_NOTMAIN", "SB200_TC_NOV8"])
+@pytest.mark.parametrize("knob", ["SB200_TC_NOTMAST", "SB200_TC_NOTMAIN", "SB200_TC_NOV8", "SB200_TC_NOCAT"])
 def test_conv_kernel_variants_stay_correct(knob, lib_built):
-    """The opt-in formulations (tap-stacked transposed kernel, stacked-tap mode) and the fallbacks of the default path
-    (no TMA-staged epilogue, cp.async window loads, 128-bit epilogue accesses) implement the same ConvArgs contract.
+    """The fallbacks of the default conv path (no TMA-staged epilogue, cp.async window loads, 128-bit epilogue accesses,
+    no hi/lo-stacked weight images) implement the same ConvArgs contract.
     The planner reads the knobs from the environment, so each variant runs in its own process."""
     import subprocess
     env = dict(os.environ, **{knob: "1"})

@@ -72,7 +72,7 @@ CASES = [
     (20480, 192, 384, 5, 1, 1.0, 2, False, 1.0, False, 20000),
     (20480 + 128, 192, 384, 1, 1, 1.0, 0, False, 1.0, True, None),
     (9 * 148 * 128 // 4, 128, 128, 3, 2, 0.1, 0, True, 1.0, False, None),
-    # tap-stacked 32-channel kernel (conv_ts.cu): every (k, dilation) of ResBlock2 / ResBlock1, ragged tails,
+    # 32-channel layers (TMA-staged epilogue, cat mode): every (k, dilation) of ResBlock2 / ResBlock1, ragged tails,
     # accumulate / residual / scale, many tiles per CTA on both accumulator stages
     (300, 32, 32, 3, 2, 0.1, 0, True, 1.0, False, 290),
     (1000, 32, 32, 5, 2, 0.1, 0, True, 1.0, False, 777),
@@ -81,7 +81,7 @@ CASES = [
     (148 * 56 * 5 + 17, 32, 32, 7, 12, 0.1, 0, True, 1 / 3, True, 148 * 56 * 5),
     (148 * 126 * 4 + 100, 32, 32, 3, 1, 0.1, 0, True, 1.0, False, None),
     (148 * 110 * 3 + 5, 32, 32, 7, 5, 0.1, 1, False, 1.0, False, None),
-    (40000, 32, 32, 11, 1, 0.1, 0, True, 1.0, False, None),      # k > 8: falls back to conv_tc
+    (40000, 32, 32, 11, 1, 0.1, 0, True, 1.0, False, None),
     # TMA-staged epilogue (conv_tc MODE 2) with nothing to fetch: the staging tile is rewritten every tile, so the
     # agent's "store has been read out" signal is the only thing that orders it (regression: WAR race)
     (148 * 128 * 6 + 77, 32, 32, 3, 1, 0.1, 0, False, 1.0, False, None),

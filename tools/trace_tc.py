@@ -1,4 +1,4 @@
-"""Per-role clock64() timeline of conv_tc_kernel / conv_ts_kernel (CTA 0, pipeline 0, first 48 tiles).
+"""Per-role clock64() timeline of conv_tc_kernel (CTA 0, pipeline 0, first 48 tiles).
 
 The probes are compiled in only with -DSB200_TC_TRACE_BUILD, so build a second library and point the loader at it:
 
