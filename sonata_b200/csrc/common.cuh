@@ -11,6 +11,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <mutex>
 
 #define SB_MAX_TAPS 16
@@ -95,16 +96,23 @@ struct PerDeviceOnce {
     }
 };
 
+// Experiment knobs of the launch planners come from the environment.  getenv() scans the whole environment block
+// (~1 us), and a planner runs twice per launch with up to seven knobs: 170 launches of a single-utterance call spent
+// more host time there than the GPU needed for the kernels.  Each knob is read ONCE per process.
+#define SB_ENV_ONCE(name) ([]() -> const char* { static const char* v = getenv(name); return v; }())
+
 void launch_conv_simt(const ConvArgs& a, cudaStream_t st);
 int conv_simt_bn_for(int cout);
 bool conv_tc_supported(const ConvArgs& a);
 void launch_conv_tc(const ConvArgs& a, cudaStream_t st);
+bool try_launch_conv_tc(const ConvArgs& a, cudaStream_t st);
 size_t conv_tc_weight_floats(int cin, int cout, int ntaps, int nt);
 void conv_tc_build_weights(const float* wt, int ldw, int cin, int cout, int ntaps, int nt, float* out);
 size_t conv_tc_cat_weight_floats(int cin, int cout, int ntaps, int nt);
 void conv_tc_build_weights_cat(const float* wt, int ldw, int cin, int cout, int ntaps, int nt, float* out);
 bool conv_tf_supported(const ConvArgs& a);
 void launch_conv_tf(const ConvArgs& a, cudaStream_t st);
+bool try_launch_conv_tf(const ConvArgs& a, cudaStream_t st);
 size_t conv_tf_weight_floats(int cin, int cout, int ntaps);
 void conv_tf_build_weights(const float* wt, int ldw, int cin, int cout, int ntaps, float* out);
 bool gemm_tf_supported(const TfGemm& g);

@@ -596,7 +596,7 @@ bool make_in_map(CUtensorMap* tm, const float* base, int rows, int cin, int ld, 
 
 // 256-bit epilogue accesses need 32-byte aligned rows and column blocks for every operand that is used
 bool epi_v8_ok(const ConvArgs& a) {
-    if (getenv("SB200_TC_NOV8")) return false;
+    if (SB_ENV_ONCE("SB200_TC_NOV8")) return false;
     auto al = [](const void* p, int ld) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 31) == 0 && (ld & 7) == 0); };
     const int half = a.act == ACT_GATE ? 2 : 1;       // the gate halves the column index
     if (a.split % (8 * half) != 0 && a.split < a.cout) return false;
@@ -609,7 +609,7 @@ bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem) {
     L.nt = a.tc_nt;
     L.v8 = epi_v8_ok(a) ? 1 : 0;
     L.tma_st = (L.v8 && a.cout == 32 && L.nt == 32 && a.act != ACT_GATE && !a.phase_cols && a.split >= a.cout && a.orow_mul == 1 &&
-                tensor_map_encoder() != nullptr && !getenv("SB200_TC_NOTMAST")) ? 1 : 0;
+                tensor_map_encoder() != nullptr && !SB_ENV_ONCE("SB200_TC_NOTMAST")) ? 1 : 0;
     if (a.res && (a.ldres & 3)) L.tma_st = 0;
     L.win = (128 + a.span + 7) & ~7;
     if (L.win * 4 > TC_MAXCH * TC_GROUP) return false;
@@ -623,12 +623,12 @@ bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem) {
     const int per_tile = (a.cin / 32) * a.ntaps;
     const size_t budget = 225 * 1024 - 2048;
     const size_t bar_bytes = (2 * TC_MAX_WRING + 6 * TC_MAX_ASTAGES + 12) * 8 + 16 + (L.tma_st ? 4 * TC_OUT_BYTES : 0);
-    L.bulk_in = (getenv("SB200_TC_NOBULKIN") == nullptr && a.ldx == 32 && a.cin == 32) ? 1 : 0;
+    L.bulk_in = (SB_ENV_ONCE("SB200_TC_NOBULKIN") == nullptr && a.ldx == 32 && a.cin == 32) ? 1 : 0;
     L.tma_in = (tensor_map_encoder() != nullptr && L.win <= 256 && (a.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0 &&
-                !getenv("SB200_TC_NOTMAIN")) ? 1 : 0;
+                !SB_ENV_ONCE("SB200_TC_NOTMAIN")) ? 1 : 0;
     L.resident = (L.ntiles_n == 1 && per_tile <= TC_MAX_WRING && per_tile * w_stage + 4 * a_buf + bar_bytes <= budget) ? 1 : 0;
     const int wper_cat = (a.cin / 32) * ((a.ntaps + 1) / 2);
-    if (a.wcat && L.tma_st && L.nt <= 64 && L.resident && wper_cat * 2 * w_stage + 4 * a_buf + bar_bytes <= budget && !getenv("SB200_TC_NOCAT")) {
+    if (a.wcat && L.tma_st && L.nt <= 64 && L.resident && wper_cat * 2 * w_stage + 4 * a_buf + bar_bytes <= budget && !SB_ENV_ONCE("SB200_TC_NOCAT")) {
         L.cat = 1; L.accw = 2 * L.nt;
         L.idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * L.nt) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     }
@@ -638,12 +638,12 @@ bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem) {
     if (!L.resident && L.ws < 2) L.ws = 2;
     auto total = [&]() { return (size_t)2 * L.na * a_buf + (size_t)(L.resident ? L.ws : 2 * L.ws) * w_stage * (L.cat ? 2 : 1) + bar_bytes; };
     L.na = TC_MAX_ASTAGES;
-    { const char* e = getenv("SB200_TC_NA"); if (e) L.na = atoi(e); }     // tuning knob
+    { const char* e = SB_ENV_ONCE("SB200_TC_NA"); if (e) L.na = atoi(e); }     // tuning knob
     while (L.na > 2 && total() > budget) L.na--;
     while (!L.resident && L.ws > 2 && total() > budget) L.ws--;
     if (total() > budget) return false;
     L.depth = L.na - 1;
-    { const char* e = getenv("SB200_TC_DEPTH"); if (e && atoi(e) >= 1 && atoi(e) < L.na) L.depth = atoi(e); }
+    { const char* e = SB_ENV_ONCE("SB200_TC_DEPTH"); if (e && atoi(e) >= 1 && atoi(e) < L.na) L.depth = atoi(e); }
     smem = total() + 2048;
     return true;
 }
@@ -705,6 +705,12 @@ static int tc_num_sms() {
 }
 
 void launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
+    if (!try_launch_conv_tc(a, st)) launch_conv_simt(a, st);
+}
+
+// plans ONCE and launches; false (nothing launched) when the shape is not supported
+bool try_launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
+    if (a.cin % 32 || a.cout % 32 || a.ntaps > SB_MAX_TAPS) return false;
     static PerDeviceOnce once;
     once.run([] {
         cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -716,7 +722,7 @@ void launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     memset(&tm, 0, sizeof(tm));
     memset(&tmr, 0, sizeof(tmr));
     memset(&tmx, 0, sizeof(tmx));
-    if (!plan(a, L, smem)) { launch_conv_simt(a, st); return; }
+    if (!plan(a, L, smem)) return false;
     const int tiles = L.ntiles_m * L.ntiles_n;
     const int grid = tiles < tc_num_sms() ? tiles : tc_num_sms();
     v = a;
@@ -727,11 +733,12 @@ void launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
         conv_tc_kernel<2><<<grid, TC2_THREADS, smem, st>>>(v, L, tm, tmr, tmx);
         g_launch_count++;
         check_launch("conv_tc_tma");
-        return;
+        return true;
     }
     conv_tc_kernel<0><<<grid, TC2_THREADS, smem, st>>>(v, L, tm, tmr, tmx);
     g_launch_count++;
     check_launch("conv_tc");
+    return true;
 }
 
 // Host-side weight image builder: [n-tile][K-block][tap] images of nt rows x 128 B, row n =

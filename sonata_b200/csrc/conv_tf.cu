@@ -423,7 +423,7 @@ bool plan(const ConvArgs& a, TfLaunch& L, size_t& smem) {
     L.ntiles_mp = (a.rows_q + 255) / 256;
     L.ntiles_n = a.cout / L.nth;
     L.chunk_kb = a.ntaps == 1 ? 2 : 1;
-    { const char* e = getenv("SB200_TF_CHUNK"); if (e && atoi(e) >= 1) L.chunk_kb = atoi(e); }     // accuracy experiments
+    { const char* e = SB_ENV_ONCE("SB200_TF_CHUNK"); if (e && atoi(e) >= 1) L.chunk_kb = atoi(e); }     // accuracy experiments
     L.tmem_cols = 32;
     while (L.tmem_cols < 4 * L.nth) L.tmem_cols <<= 1;
     // kind::tf32 instruction descriptor: D fp32 (1<<4), A = B = TF32 (2<<7, 2<<10), K-major both, N>>3, M>>4
@@ -443,7 +443,7 @@ bool plan(const ConvArgs& a, TfLaunch& L, size_t& smem) {
         while (L.nw < TF_NW_MAX && L.nw < 2 * a.ntaps + 2) { L.nw++; if (total() > budget) { L.nw--; break; } }
         while (L.na < TF_NA_MAX) { L.na++; if (total() > budget) { L.na--; break; } }
     }
-    { const char* e = getenv("SB200_TF_NW"); if (e && atoi(e) >= 2 && atoi(e) <= TF_NW_MAX) { const int o = L.nw; L.nw = atoi(e); if (total() > budget) L.nw = o; } }
+    { const char* e = SB_ENV_ONCE("SB200_TF_NW"); if (e && atoi(e) >= 2 && atoi(e) <= TF_NW_MAX) { const int o = L.nw; L.nw = atoi(e); if (total() > budget) L.nw = o; } }
     smem = total() + 1024;
     return true;
 }
@@ -469,6 +469,11 @@ bool conv_tf_supported(const ConvArgs& a) {
 }
 
 void launch_conv_tf(const ConvArgs& a, cudaStream_t st) {
+    if (!try_launch_conv_tf(a, st)) launch_conv_simt(a, st);
+}
+
+// plans ONCE and launches; false (nothing launched) when the shape is not supported
+bool try_launch_conv_tf(const ConvArgs& a, cudaStream_t st) {
     static PerDeviceOnce once;
     once.run([] {
         cudaFuncSetAttribute(conv_tf_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -477,15 +482,14 @@ void launch_conv_tf(const ConvArgs& a, cudaStream_t st) {
     TfLaunch L; size_t smem;
     CUtensorMap tmx;
     if (!plan(a, L, smem) ||
-        !tensor_map_2d(&tmx, a.x, (unsigned long long)a.cin, (unsigned long long)a.rows_in, (unsigned long long)a.ldx, 32, (unsigned)L.win, true)) {
-        launch_conv_simt(a, st);
-        return;
-    }
+        !tensor_map_2d(&tmx, a.x, (unsigned long long)a.cin, (unsigned long long)a.rows_in, (unsigned long long)a.ldx, 32, (unsigned)L.win, true))
+        return false;
     const int tiles = L.ntiles_mp * L.ntiles_n;
     const int grid = tiles < tf_num_sms() ? tiles : tf_num_sms();
     conv_tf_kernel<0><<<grid, TfCfg<0>::THREADS, smem, st>>>(a, L, tmx, tmx, nullptr);
     g_launch_count++;
     check_launch("conv_tf");
+    return true;
 }
 
 bool gemm_tf_supported(const TfGemm& g) {

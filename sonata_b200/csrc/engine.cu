@@ -204,12 +204,13 @@ struct Runner {
         p.y0 = o.y0; p.ldy0 = o.ldy0; p.acc0 = o.acc0; p.split = o.split < 0 ? w.cout : o.split;
         p.y1 = o.y1; p.ldy1 = o.ldy1; p.acc1 = o.acc1;
         p.yt = o.yt; p.yt_col0 = o.yt_col0; p.ldyt = o.ldyt;
-        if (o.yt && !(v.backend == 1 && o.tf_ok && conv_tf_supported(p)))
-            throw Error(19, "internal: a transposed conv output needs the conv_tf kernel");
+
         // backend 1 (default): tcgen05 everywhere; 2: tcgen05 flow / decoder, fp32 CUDA cores for the text encoder and
         // the duration predictor (the round-1 configuration, kept for A/B runs); 0: fp32 CUDA cores everywhere
-        if (v.backend == 1 && o.tf_ok && conv_tf_supported(p)) launch_conv_tf(p, st);
-        else if (v.backend >= 1 && o.tc_ok && conv_tc_supported(p)) launch_conv_tc(p, st);
+        // (each try_launch plans once and returns false without launching when the shape is not supported)
+        if (v.backend == 1 && o.tf_ok && try_launch_conv_tf(p, st)) {}
+        else if (o.yt) throw Error(19, "internal: a transposed conv output needs the conv_tf kernel");
+        else if (v.backend >= 1 && o.tc_ok && try_launch_conv_tc(p, st)) {}
         else launch_conv_simt(p, st);
         const double vr = (double)lin.valid_rows;
         const int cout_w = (o.act == ACT_GATE) ? w.cout / 2 : w.cout;
@@ -282,8 +283,7 @@ void run_decoder(Runner& R, const Level& LY, const float* s, float* d_wav, const
             pa.rows_q = Lin.map.rows; pa.orow_mul = st.u; pa.orow_add = 0; pa.phase_cols = st.cout;
             pa.map = Lin.map; pa.act = ACT_NONE; pa.scale = 1.f;
             pa.y0 = up; pa.ldy0 = st.cout; pa.split = st.fused.cout; pa.y1 = up; pa.ldy1 = st.cout;
-            if (conv_tc_supported(pa)) {
-                launch_conv_tc(pa, R.st);
+            if (try_launch_conv_tc(pa, R.st)) {
                 const double vr = (double)Lin.valid_rows;
                 R.count(2.0 * vr * st.cin * st.cout * st.k, 4.0 * (vr * (st.cin + (double)st.u * st.cout) + (double)st.cin * st.cout * st.k));
                 fused_done = true;
