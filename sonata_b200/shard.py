@@ -21,13 +21,14 @@ import torch.distributed as dist
 def lpt_partition(costs: Sequence[float], world: int) -> List[List[int]]:
     """Longest-processing-time greedy: sort by cost descending, give each to the least loaded rank.
     Cost ~ T_x (frames ~ 3 T_x).  Returns, per rank, utterance indices in ascending order."""
+    import heapq
     order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
-    load = [0.0] * world
+    heap = [(0.0, r) for r in range(world)]           # (load, rank): ties go to the lowest rank
     parts: List[List[int]] = [[] for _ in range(world)]
     for i in order:
-        r = min(range(world), key=lambda k: (load[k], k))
+        load, r = heapq.heappop(heap)
         parts[r].append(i)
-        load[r] += costs[i]
+        heapq.heappush(heap, (load + costs[i], r))
     return [sorted(p) for p in parts]
 
 
@@ -221,38 +222,73 @@ class Frontend:
         self.model, self.group, self.pcm16 = model, group, pcm16
         self.seg = SharedSegment(group, pin)
         self.run_local = run_local
-        self._payload = None           # device buffer for the id broadcast
-        self._lens = None              # device buffer for the sample-count all-reduce
+        self._payload = None           # device buffer for the id broadcast (first block)
+        self._host = None              # page-locked host staging of the same
+        self._big = None               # device buffer for inputs beyond the first block
+        self._lens = None              # device / page-locked host buffers for the sample-count all-reduce
+        self._lens_h = None
         self.last_device_ms = 0.0
         self.last_table = None
         self.collect_profile = False   # keep the per-region device times of the last local pass (bench.py)
         self.last_profile = []
 
     # -- collective plumbing ----------------------------------------------------------------------------------------
+    FIRST_BLOCK = 1 << 18      # int64 elements (2 MB) of the first broadcast: [n, total, lens, owner, ids ...]
+
     def _bcast_ids(self, batches):
+        """ONE broadcast of a fixed-size block carries the header and (for up to ~260k ids) everything else; a second
+        broadcast follows only for larger inputs.  Host staging buffers are page-locked and reused."""
         rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
         dev = _dev(self.group)
-        meta = torch.zeros(2, dtype=torch.int64, device=dev)
+        fb = self.FIRST_BLOCK
+        if self._payload is None:
+            self._payload = torch.empty(fb, dtype=torch.int64, device=dev)
+            pin = dev.type == "cuda"
+            self._host = torch.empty(fb, dtype=torch.int64, pin_memory=pin)
+        total = 0
         if rank == 0:
-            lens = np.array([len(b) for b in batches], dtype=np.int64)
+            lens = np.fromiter((len(b) for b in batches), dtype=np.int64, count=len(batches))
             owner = np.zeros(len(batches), dtype=np.int64)
             for r, p in enumerate(lpt_partition(lens.tolist(), world)):
                 owner[p] = r
-            flat = np.concatenate([lens, owner] + [np.asarray(b, dtype=np.int64) for b in batches])
-            meta = torch.tensor([len(batches), flat.size], dtype=torch.int64).to(dev)
-        dist.broadcast(meta, 0, group=self.group)
-        n, total = (int(x) for x in meta.cpu().tolist())
-        if self._payload is None or self._payload.numel() < total:
-            self._payload = torch.empty(max(int(total * 1.5), 1 << 16), dtype=torch.int64, device=dev)
-        buf = self._payload[:total]
-        if rank == 0:
-            buf.copy_(torch.from_numpy(flat))
-        dist.broadcast(buf, 0, group=self.group)
-        flat = buf.cpu().numpy()
-        lens, owner = flat[:n], flat[n:2 * n]
-        offs = 2 * n + np.concatenate([[0], np.cumsum(lens)])
+            total = 2 + 2 * len(batches) + int(lens.sum())
+            if self._host.numel() < total:
+                self._host = torch.empty(int(total * 1.5), dtype=torch.int64, pin_memory=self._host.is_pinned())
+            h = self._host.numpy()
+            h[0], h[1] = len(batches), total
+            n0 = len(batches)
+            h[2:2 + n0] = lens
+            h[2 + n0:2 + 2 * n0] = owner
+            np.concatenate([np.asarray(b, dtype=np.int64) for b in batches], out=h[2 + 2 * n0:total])
+            self._payload.copy_(self._host[:fb], non_blocking=True)
+        dist.broadcast(self._payload, 0, group=self.group)
+        if rank != 0:
+            self._host[:fb].copy_(self._payload, non_blocking=True)
+            if dev.type == "cuda":
+                torch.cuda.current_stream().synchronize()
+            total = int(self._host[1])
+        if total > fb:                                   # rare: more than one block of ids
+            total_t = total
+            if self._big is None or self._big.numel() < total_t - fb:
+                self._big = torch.empty(int((total_t - fb) * 1.5), dtype=torch.int64, device=dev)
+            rest = self._big[:total_t - fb]
+            if rank == 0:
+                rest.copy_(self._host[fb:total_t])
+            dist.broadcast(rest, 0, group=self.group)
+            if rank != 0:
+                if self._host.numel() < total_t:
+                    nh = torch.empty(int(total_t * 1.5), dtype=torch.int64, pin_memory=self._host.is_pinned())
+                    nh[:fb] = self._host[:fb]
+                    self._host = nh
+                self._host[fb:total_t].copy_(rest)
+                if dev.type == "cuda":
+                    torch.cuda.current_stream().synchronize()
+        flat = self._host.numpy()
+        n = int(flat[0])
+        lens, owner = flat[2:2 + n], flat[2 + n:2 + 2 * n].copy()
+        offs = 2 + 2 * n + np.concatenate([[0], np.cumsum(lens)])
         mine = np.nonzero(owner == rank)[0]
-        return n, owner, mine, [flat[offs[i]:offs[i + 1]] for i in mine]
+        return n, owner, mine, [flat[offs[i]:offs[i + 1]].copy() for i in mine]
 
     def synthesize(self, batches: Optional[Sequence[np.ndarray]], device_only: bool = False):
         """Collective.  Rank 0 passes every utterance's ids and gets the waveforms back in utterance order (views into
@@ -278,13 +314,20 @@ class Frontend:
         else:
             samples_local = self.run_local(my_ids, None, 0, fmt) if my_ids else []
         if self._lens is None or self._lens.numel() < n:
-            self._lens = torch.zeros(max(n, 1024), dtype=torch.int64, device=dev)
-        lens_t = self._lens[:n]
-        lens_t.zero_()
+            cap = max(n, 1024)
+            self._lens = torch.zeros(cap, dtype=torch.int64, device=dev)
+            self._lens_h = torch.zeros(cap, dtype=torch.int64, pin_memory=dev.type == "cuda")
+        lh = self._lens_h.numpy()
+        lh[:n] = 0
         if len(mine):
-            lens_t[torch.from_numpy(mine).to(dev)] = torch.tensor(list(samples_local), dtype=torch.int64).to(dev)
+            lh[mine] = np.asarray(samples_local, dtype=np.int64)
+        lens_t = self._lens[:n]
+        lens_t.copy_(self._lens_h[:n], non_blocking=True)
         dist.all_reduce(lens_t, group=self.group)
-        samples = lens_t.cpu().numpy()
+        self._lens_h[:n].copy_(lens_t, non_blocking=True)
+        if dev.type == "cuda":
+            torch.cuda.current_stream().synchronize()
+        samples = lh[:n].copy()
         self.last_table = (owner, samples)
         if device_only:
             if job is not None:
