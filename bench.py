@@ -225,6 +225,8 @@ def main():
         from sonata_b200 import build as _b
         _b.build()
     torch.cuda.set_device(local_rank)
+    orig_affinity = os.sched_getaffinity(0)
+    numa_node = None if os.environ.get("SB200_NO_NUMA_BIND") else shard.bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if rank == 0:
@@ -416,6 +418,12 @@ def main():
         mrf_bytes = sum(v["bytes"] for v in mrf.values()); mrf_flops = sum(v["flops"] for v in mrf.values())
         all_ms = sum(v["ms"] for v in prof_acc.values())
         ach_gbs = mrf_bytes / (mrf_ms * 1e-3) / 1e9 if mrf_ms else 0.0
+        arch = voicegen.ARCH[quality]
+        frames_rank0 = audio_local * SR / HOP              # frames this rank decoded in the timed steps
+        fused_bytes, U_, C_ = 0.0, 1, arch["up_init"]
+        for u_ in arch["up_rates"]:
+            U_ *= u_; C_ //= 2
+            fused_bytes += 2.0 * frames_rank0 * U_ * C_ * 4
         roofline = {
             "bound": "hbm", "kernel": ("conv_tc_kernel" if args.backend >= 1 else "conv_simt_kernel") + " on dec.mrf* (HiFi-GAN ResBlock dilated Conv1d + residual; largest share of the step)",
             "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"],
@@ -426,6 +434,11 @@ def main():
             "share_of_step": mrf_ms / all_ms if all_ms else None,
             "achieved_tflops": mrf_flops / (mrf_ms * 1e-3) / 1e12 if mrf_ms else 0.0,
             "tensor_peak_tflops": peaks["bf16_tflops_sustained"],
+            # the same time against the bytes of a FUSED stage (x in + mean out once per stage, fp32): how far the
+            # layer-wise formulation is from what a fully fused ResBlock stage would have to move (DESIGN.md section 3
+            # explains why the stages stay layer-wise: shared-memory capacity)
+            "fused_stage_bytes_per_step": fused_bytes / args.steps if mrf_ms else None,
+            "fused_stage_frac": (fused_bytes / (mrf_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if mrf_ms else None,
             "note": "algorithmic bytes = each conv's input + output (+ the residual when it is NOT the conv input, + the accumulated buffer when read-modify-written) once, fp32, + weights; "
                     "FLOPs at 2/MAC over valid rows",
         }
@@ -434,6 +447,7 @@ def main():
                    for k, v in prof_acc.items()}
         cpu_base = None
         if not args.no_cpu_baseline and world == 1:
+            os.sched_setaffinity(0, orig_affinity)         # the CPU arm may use every host core
             n_s = 4
             threads = tune_cpu_threads(quality, cores)
             a_, w_ = cpu_reference(quality, NPH, n_s, threads)
@@ -455,7 +469,8 @@ def main():
                     "path": ("public call speak_batch_ids: host ids -> pinned host waveforms" if world == 1 else
                              "ONE frontend on rank 0: NCCL broadcast of the ids, per-rank batched pass, NCCL all-reduce of the frame "
                              "counts, device->host copies into one page-locked host segment shared by the ranks"),
-                    "per_rank_replicas": replicas_value},
+                    "per_rank_replicas": replicas_value,
+                    "numa_node_bound": numa_node},
             "roofline": roofline, "regions": regions, "cpu_baseline": cpu_base, "c5": c5, "secondary": secondary or None,
         }
         sys.stdout.flush()
