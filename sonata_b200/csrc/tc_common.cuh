@@ -6,6 +6,10 @@
 #include <cuda_bf16.h>
 #include <stdio.h>
 
+#ifndef SB200_MBAR_HINT_NS
+#define SB200_MBAR_HINT_NS 20000
+#endif
+
 namespace sb200 {
 namespace tcx {
 
@@ -34,8 +38,8 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");   // suspend-time hint (ns): a waiting warp
-                                                                         // sleeps in hardware instead of spinning
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"((unsigned)SB200_MBAR_HINT_NS) : "memory");   // suspend-time hint (ns): a waiting
+                                                                         // warp sleeps in hardware instead of spinning
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
