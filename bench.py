@@ -225,8 +225,6 @@ def main():
         from sonata_b200 import build as _b
         _b.build()
     torch.cuda.set_device(local_rank)
-    orig_affinity = os.sched_getaffinity(0)
-    numa_node = None if os.environ.get("SB200_NO_NUMA_BIND") else shard.bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if rank == 0:
@@ -447,7 +445,6 @@ def main():
                    for k, v in prof_acc.items()}
         cpu_base = None
         if not args.no_cpu_baseline and world == 1:
-            os.sched_setaffinity(0, orig_affinity)         # the CPU arm may use every host core
             n_s = 4
             threads = tune_cpu_threads(quality, cores)
             a_, w_ = cpu_reference(quality, NPH, n_s, threads)
@@ -469,8 +466,7 @@ def main():
                     "path": ("public call speak_batch_ids: host ids -> pinned host waveforms" if world == 1 else
                              "ONE frontend on rank 0: NCCL broadcast of the ids, per-rank batched pass, NCCL all-reduce of the frame "
                              "counts, device->host copies into one page-locked host segment shared by the ranks"),
-                    "per_rank_replicas": replicas_value,
-                    "numa_node_bound": numa_node},
+                    "per_rank_replicas": replicas_value},
             "roofline": roofline, "regions": regions, "cpu_baseline": cpu_base, "c5": c5, "secondary": secondary or None,
         }
         sys.stdout.flush()

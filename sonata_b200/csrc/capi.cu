@@ -21,15 +21,19 @@ std::mutex g_pin_mu;
 std::deque<PinnedBlock*> g_pin_free;
 std::unordered_map<const float*, PinnedBlock*> g_owner;   // audio.data -> block
 
+// Smallest pooled block that fits (a larger one is fine: an exact-size policy made a caller that alternates between
+// big and small batches pay cudaMallocHost + cudaFreeHost, ~1 ms, on every small call).
 PinnedBlock* pin_acquire(size_t bytes) {
     {
         std::lock_guard<std::mutex> g(g_pin_mu);
+        auto best = g_pin_free.end();
         for (auto it = g_pin_free.begin(); it != g_pin_free.end(); ++it)
-            if ((*it)->bytes >= bytes && (*it)->bytes <= 2 * bytes + (1 << 20)) {
-                PinnedBlock* b = *it;
-                g_pin_free.erase(it);
-                return b;
-            }
+            if ((*it)->bytes >= bytes && (best == g_pin_free.end() || (*it)->bytes < (*best)->bytes)) best = it;
+        if (best != g_pin_free.end()) {
+            PinnedBlock* b = *best;
+            g_pin_free.erase(best);
+            return b;
+        }
     }
     PinnedBlock* b = new PinnedBlock();
     b->bytes = bytes + bytes / 8 + 4096;
@@ -39,9 +43,13 @@ PinnedBlock* pin_acquire(size_t bytes) {
     return b;
 }
 void pin_release(PinnedBlock* b) {
-    std::lock_guard<std::mutex> g(g_pin_mu);
-    if (g_pin_free.size() >= 4) { cudaFreeHost(b->base); delete b; return; }
-    g_pin_free.push_back(b);
+    PinnedBlock* victim = nullptr;
+    {
+        std::lock_guard<std::mutex> g(g_pin_mu);
+        g_pin_free.push_back(b);
+        if (g_pin_free.size() > 8) { victim = g_pin_free.front(); g_pin_free.pop_front(); }     // oldest goes
+    }
+    if (victim) { cudaFreeHost(victim->base); delete victim; }
 }
 
 char* dup_cstr(const std::string& s) {

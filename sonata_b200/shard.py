@@ -371,29 +371,3 @@ def sharded_synthesize(batches: Optional[Sequence[np.ndarray]], synth: Callable[
         local = torch.zeros(0, dtype=torch.float32, device=dev)
     return gather_waveforms(local, [len(w) for w in waves], group)
 
-
-def bind_to_gpu_numa_node(device: int) -> Optional[int]:
-    """Deployment plumbing (what `numactl --cpunodebind` does for a per-GPU worker): pin this process to the CPUs of the
-    NUMA node its GPU hangs off, BEFORE any page-locked buffer is allocated, so that result buffers are first-touched on
-    that node and device->host copies do not cross the socket interconnect.  Returns the node, or None when the
-    topology is not exposed (then nothing changes)."""
-    try:
-        p = torch.cuda.get_device_properties(device)
-        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
-        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
-            node = int(f.read().strip())
-        if node < 0:
-            return None
-        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
-            spec = f.read().strip()
-        cpus = set()
-        for part in spec.split(","):
-            lo, _, hi = part.partition("-")
-            cpus.update(range(int(lo), int(hi or lo) + 1))
-        allowed = cpus & os.sched_getaffinity(0)
-        if not allowed:
-            return None
-        os.sched_setaffinity(0, allowed)
-        return node
-    except Exception:       # noqa: BLE001  (no sysfs, no permission, exotic topology: leave the affinity alone)
-        return None
