@@ -535,40 +535,84 @@ __global__ void __launch_bounds__(256) expand_kernel(const float* __restrict__ s
 }
 
 // ------------------------------------------------------------------ conv_post + tanh (C -> 1, k = 7)
-// oracle: decoder() tail.  One thread per output sample; a CTA stages its rows (+3 halo) in smem.
+// oracle: decoder() tail.  HBM-bound in principle (read 4*C bytes, write 4 bytes per sample); the first version (one
+// sample per thread, 7*C scalar shared-memory loads each) was bound by shared-memory wavefronts at 0.70 ms on C2 against
+// a 0.3 ms HBM floor.  Here a CTA stages 512 rows CHANNEL-MAJOR (xs[c][row], leaky-relu applied) and every thread
+// produces FOUR consecutive samples: per channel three 128-bit loads bring the 12 staged rows its 4 x 7 taps touch, so a
+// staged value is read ~once instead of seven times.  Layout: 16-byte unit u (4 rows) of channel c lives at unit
+// (u ^ ((c >> 2) & 7)) -- with that XOR both the transposing stores of the load phase (8 channel groups x 4 rows per
+// warp) and the unit-strided 128-bit loads of the compute phase are bank-conflict free.  256 threads: all of them load
+// (four independent 128-bit loads in flight each), pairs of lanes split the channels of one 4-sample group.
 template <int C>
 __global__ void __launch_bounds__(256) conv_post_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         float* __restrict__ wav, const FrameSeg* __restrict__ fsegs,
-                                                        const int* __restrict__ ftile_seg, int U, RowMap map) {
-    constexpr int ROWS = 256, HALO = 3, ST = C + 1;
-    extern __shared__ float sm[];
-    float* xs = sm;                       // [(ROWS+2*HALO)][C+1], leaky-relu(0.01) applied
-    float* ws = xs + (ROWS + 2 * HALO) * ST;   // [7][C]
+                                                        const int* __restrict__ ftile_seg, int U, RowMap map, int vec_ok) {
+    constexpr int NT = 256, ROWS = 512, LEAD = 4, SR = ROWS + 8;   // staged rows r0-4 .. r0+515
+    constexpr int S = 544;                               // floats per channel row: 136 units, a multiple of 8 units >= SR/4 + 7
+    extern __shared__ __align__(16) float sm[];
+    float* xs = sm;                       // [C][S]
+    float* ws = xs + C * S;               // [C][8]: taps 0..6 of channel c, then 0
+    const int tid = threadIdx.x;
     const int r0 = blockIdx.x * ROWS;
-    for (int i = threadIdx.x; i < 7 * C; i += 256) ws[i] = w[i];
-    for (int i = threadIdx.x; i < (ROWS + 2 * HALO) * (C / 4); i += 256) {
-        const int rr = i / (C / 4), c4 = i % (C / 4);
-        const int gr = r0 - HALO + rr;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gr >= 0 && gr < map.rows) v = reinterpret_cast<const float4*>(x + (size_t)gr * C)[c4];
-        float* d = xs + rr * ST + c4 * 4;
-        d[0] = v.x > 0.f ? v.x : 0.01f * v.x;
-        d[1] = v.y > 0.f ? v.y : 0.01f * v.y;
-        d[2] = v.z > 0.f ? v.z : 0.01f * v.z;
-        d[3] = v.w > 0.f ? v.w : 0.01f * v.w;
+    for (int i = tid; i < C * 8; i += NT) {
+        const int c = i >> 3, t = i & 7;
+        ws[i] = t < 7 ? w[t * C + c] : 0.f;
+    }
+    constexpr int NF4 = SR * (C / 4);
+    for (int base = tid; base < NF4; base += NT * 4) {    // four independent 128-bit loads in flight per thread
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int i = base + k * NT;
+            const int rr = i / (C / 4), c4 = i % (C / 4);
+            const int gr = r0 - LEAD + rr;
+            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < NF4 && gr >= 0 && gr < map.rows) v[k] = reinterpret_cast<const float4*>(x + (size_t)gr * C)[c4];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int i = base + k * NT;
+            if (i >= NF4) continue;
+            const int rr = i / (C / 4), c4 = i % (C / 4);
+            const int pos = (((rr >> 2) ^ (c4 & 7)) << 2) | (rr & 3);
+            float* d = xs + (size_t)(c4 * 4) * S + pos;
+            d[0] = v[k].x > 0.f ? v[k].x : 0.01f * v[k].x;
+            d[S] = v[k].y > 0.f ? v[k].y : 0.01f * v[k].y;
+            d[2 * S] = v[k].z > 0.f ? v[k].z : 0.01f * v[k].z;
+            d[3 * S] = v[k].w > 0.f ? v[k].w : 0.01f * v[k].w;
+        }
     }
     __syncthreads();
-    const int r = r0 + threadIdx.x;
-    if (r >= map.rows || !row_valid(map, r)) return;
-    float acc = 0.f;
+    // thread pair (2g, 2g+1) owns the four rows r0 + 4g ..; each lane of the pair sums half of the channels
+    const int g = tid >> 1, half = tid & 1;
+    const int r = r0 + 4 * g;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int u0 = g + 1;                                     // staged unit of the group's own four rows
+#pragma unroll 4
+    for (int k = 0; k < C / 2; k++) {
+        const int c = half * (C / 2) + k;
+        const int sw = (c >> 2) & 7;
+        const float* xc = xs + (size_t)c * S;
+        const float4 a = *reinterpret_cast<const float4*>(xc + (((u0 - 1) ^ sw) << 2));
+        const float4 b = *reinterpret_cast<const float4*>(xc + ((u0 ^ sw) << 2));
+        const float4 d = *reinterpret_cast<const float4*>(xc + (((u0 + 1) ^ sw) << 2));
+        const float4 w0 = *reinterpret_cast<const float4*>(ws + c * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(ws + c * 8 + 4);
+        const float v[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y, d.z, d.w};
+        const float wt[7] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z};
 #pragma unroll
-    for (int t = 0; t < 7; t++) {
-        const float* xr = xs + (threadIdx.x + t) * ST;
-#pragma unroll 8
-        for (int c = 0; c < C; c++) acc = fmaf(xr[c], ws[t * C + c], acc);
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int t = 0; t < 7; t++) acc[j] = fmaf(v[j + 1 + t], wt[t], acc[j]);
     }
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 1);
+    if (half != 0 || r >= map.rows || !row_valid(map, r)) return;     // a group of four rows never straddles a segment end
     const FrameSeg fs = fsegs[ftile_seg[r / map.gran]];
-    wav[fs.out_off + (long long)(r - (long long)fs.off * U)] = tanhf(acc);
+    float* dst = wav + fs.out_off + (long long)(r - (long long)fs.off * U);
+    const float o0 = tanhf(acc[0]), o1 = tanhf(acc[1]), o2 = tanhf(acc[2]), o3 = tanhf(acc[3]);
+    if (vec_ok) *reinterpret_cast<float4*>(dst) = make_float4(o0, o1, o2, o3);
+    else { dst[0] = o0; dst[1] = o1; dst[2] = o2; dst[3] = o3; }
 }
 
 // ------------------------------------------------------------------ f32 -> i16 with per-utterance peak normalisation
@@ -775,12 +819,14 @@ void launch_expand(const float* stats, int ldst, int I, const int* cum, const fl
 
 void launch_conv_post(const float* x, int C, const float* w, float* wav, const FrameSeg* fsegs,
                       const int* ftile_seg, int U, RowMap map, cudaStream_t st) {
-    const unsigned grid = (map.rows + 255) / 256;
-    const size_t smem = sizeof(float) * ((size_t)(256 + 6) * (C + 1) + 7 * C);
+    if (U % 4 != 0) throw_launch_error("conv_post: samples per frame must be a multiple of 4");
+    const unsigned grid = (map.rows + 511) / 512;
+    const size_t smem = sizeof(float) * ((size_t)C * 544 + (size_t)C * 8);
+    const int vec_ok = (reinterpret_cast<uintptr_t>(wav) & 15) == 0;     // out_off is a multiple of U samples
     switch (C) {
-        case 16: set_smem(conv_post_kernel<16>, smem); conv_post_kernel<16><<<grid, 256, smem, st>>>(x, w, wav, fsegs, ftile_seg, U, map); break;
-        case 32: set_smem(conv_post_kernel<32>, smem); conv_post_kernel<32><<<grid, 256, smem, st>>>(x, w, wav, fsegs, ftile_seg, U, map); break;
-        case 64: set_smem(conv_post_kernel<64>, smem); conv_post_kernel<64><<<grid, 256, smem, st>>>(x, w, wav, fsegs, ftile_seg, U, map); break;
+        case 16: set_smem(conv_post_kernel<16>, smem); conv_post_kernel<16><<<grid, 256, smem, st>>>(x, w, wav, fsegs, ftile_seg, U, map, vec_ok); break;
+        case 32: set_smem(conv_post_kernel<32>, smem); conv_post_kernel<32><<<grid, 256, smem, st>>>(x, w, wav, fsegs, ftile_seg, U, map, vec_ok); break;
+        case 64: set_smem(conv_post_kernel<64>, smem); conv_post_kernel<64><<<grid, 256, smem, st>>>(x, w, wav, fsegs, ftile_seg, U, map, vec_ok); break;
         default: throw_launch_error("conv_post: unsupported channel count (16 / 32 / 64)");
     }
     g_launch_count++;
