@@ -96,6 +96,30 @@ struct PerDeviceOnce {
     }
 };
 
+// Programmatic dependent launch.  The step is a chain of ~170-200 dependent kernels; at single-utterance sizes most of
+// them run for 5-30 us, so the launch gap and each kernel's prologue (mbarrier init, TMEM allocation, tensor-map fetch)
+// are a visible part of the step.  Every kernel of the library is launched with the programmatic-stream-serialization
+// attribute and starts with pdl_wait() BEFORE its first access to global memory (tcgen05 kernels: after their prologue),
+// after a pdl_trigger() at its very top: the following kernels' CTAs may become resident and run their own prologues (and
+// fetch their weights, which no kernel writes) while this kernel is still working; their pdl_wait() returns only when the
+// preceding grid has completed and its writes are visible.  Nothing before a pdl_wait() touches memory another kernel
+// writes, and a kernel whose CTAs are all resident can always finish, so running ahead cannot deadlock.
+// SB200_NO_PDL=1 launches without the attribute (the two instructions are then no-ops).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    static const int allowed = getenv("SB200_NO_PDL") ? 0 : 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = allowed;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // Experiment knobs of the launch planners come from the environment.  getenv() scans the whole environment block
 // (~1 us), and a planner runs twice per launch with up to seven knobs: 170 launches of a single-utterance call spent
 // more host time there than the GPU needed for the kernels.  Each knob is read ONCE per process.

@@ -40,6 +40,7 @@ template <> struct Vec<2> { using T = float2; };
 
 template <int BM, int TX, int VW, int NV>
 __global__ void __launch_bounds__(256, 2) conv_simt_kernel(const ConvArgs a) {
+    pdl_trigger(); pdl_wait();
     constexpr int TY = 256 / TX;
     constexpr int TM = BM / TY;
     constexpr int TN = VW * NV;
@@ -213,7 +214,7 @@ void launch_cfg(const ConvArgs& a, cudaStream_t st) {
     once.run([&] { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); });
     const size_t smem = ((size_t)2 * (BM + a.span) * AS_STRIDE + 2 * BK * BN) * sizeof(float);
     dim3 grid((a.rows_q + BM - 1) / BM, a.ldw / BN);
-    kern<<<grid, 256, smem, st>>>(a);
+    launch_pdl(kern, dim3(grid), dim3(256), smem, st, a);
     g_launch_count++;
     check_launch("conv");
 }

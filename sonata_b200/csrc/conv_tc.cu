@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                                                                   const __grid_constant__ CUtensorMap tm_out,
                                                                   const __grid_constant__ CUtensorMap tm_res,
                                                                   const __grid_constant__ CUtensorMap tm_x) {
+    pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t a_buf = (uint32_t)L.win * 128u;              // one [hi|lo] window image
@@ -131,12 +132,24 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
     const int total_tiles = L.ntiles_m * L.ntiles_n;
     const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-    if (tid == 0) {
-        for (int s = 0; s < wslots; s++) { mbar_init(smem_u32(&w_full[s]), 1); mbar_init(smem_u32(&w_empty[s]), 1); }
-        for (int s = 0; s < 2 * TC_MAX_ASTAGES; s++) { mbar_init(smem_u32(&a_full[s]), TC_GROUP); mbar_init(smem_u32(&a_empty[s]), 1); mbar_init(smem_u32(&raw_full[s]), 1); }
-        for (int s = 0; s < 4; s++) { mbar_init(smem_u32(&acc_full[s]), 1); mbar_init(smem_u32(&acc_empty[s]), 128); }
-        for (int s = 0; s < 2; s++) { mbar_init(smem_u32(&staged[s]), 128); mbar_init(smem_u32(&epi_full[s]), 1); }
+    if (warp == 3) {
+        // all barriers are initialised by one warp in parallel (a single thread doing the ~120 inits one after the other
+        // was ~2 us of every launch); bars[] order: w_full, w_empty, a_full, a_empty, acc_full, acc_empty, raw_full,
+        // staged, epi_full
+        constexpr int NB = 2 * TC_MAX_WRING + 6 * TC_MAX_ASTAGES + 12;
+        for (int i = lane; i < NB; i += 32) {
+            const int j = i - 2 * TC_MAX_WRING;
+            const uint32_t cnt = j < 0 ? 1u : j < 8 ? (uint32_t)TC_GROUP : j < 20 ? 1u : j < 24 ? 128u : j < 32 ? 1u : j < 34 ? 128u : 1u;
+            mbar_init(smem_u32(&bars[i]), cnt);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (lane == 0) {                       // descriptor fetches overlap the rest of the prologue
+            if (L.tma_in) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
+            if (MODE == 2) {
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_out) : "memory");
+                if (a.res) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_res) : "memory");
+            }
+        }
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -147,6 +160,10 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above (barriers, TMEM, tensor-map prefetch) overlapped the previous kernels' tails; from here on global
+    // memory written by them is read -- except by the weight warps, whose bulk copies read constants (their TMA-agent
+    // part waits before its first fetch)
+    if (warp != 2 && warp != 3) pdl_wait();
 
     if (warp < 2) {
         // ===================== MMA issuer of pipeline p = warp =====================
@@ -255,6 +272,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
             // tiles of the pipeline's next tile into the same staging buffers.  The epilogue threads never wait for
             // a store and never touch global memory.
             if (lane == 0) {
+                pdl_wait();                                                           // residual / previous tiles: predecessor data
                 const uint32_t st = smem_u32(EX + (size_t)p * 2 * TC_OUT_BYTES);      // [0] residual-in / output, [1] previous
                 const uint32_t bytes = (a.res ? TC_OUT_BYTES : 0) + (a.acc0 ? TC_OUT_BYTES : 0);
                 auto fetch = [&](int tl) {
@@ -730,12 +748,12 @@ bool try_launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     if (L.tma_in && !make_in_map(&tmx, a.x, a.rows_in, a.cin, a.ldx, L.win)) L.tma_in = 0;
     if (L.tma_st && L.resident && make_out_map(&tm, a.y0 + (size_t)a.orow_add * a.ldy0, a.rows_q, a.ldy0) &&
         (!a.res || make_out_map(&tmr, const_cast<float*>(a.res) + (size_t)a.orow_add * a.ldres, a.rows_q, a.ldres))) {
-        conv_tc_kernel<2><<<grid, TC2_THREADS, smem, st>>>(v, L, tm, tmr, tmx);
+        launch_pdl(conv_tc_kernel<2>, dim3(grid), dim3(TC2_THREADS), smem, st, v, L, tm, tmr, tmx);
         g_launch_count++;
         check_launch("conv_tc_tma");
         return true;
     }
-    conv_tc_kernel<0><<<grid, TC2_THREADS, smem, st>>>(v, L, tm, tmr, tmx);
+    launch_pdl(conv_tc_kernel<0>, dim3(grid), dim3(TC2_THREADS), smem, st, v, L, tm, tmr, tmx);
     g_launch_count++;
     check_launch("conv_tc");
     return true;

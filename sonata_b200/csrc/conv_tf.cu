@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(TfCfg<GM>::THREADS, 1) conv_tf_kernel(const Co
                                                                          const TfTile* __restrict__ tiles) {
     constexpr int TF_NCONV = TfCfg<GM>::NCONV;
     constexpr int TF_WARP_EPI0 = TfCfg<GM>::WARP_EPI0;
+    pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t a_img = (uint32_t)L.win * 128u;               // one image (hi or lo) of a window
@@ -108,15 +109,25 @@ __global__ void __launch_bounds__(TfCfg<GM>::THREADS, 1) conv_tf_kernel(const Co
     auto tile_nkb = [&](int tl) -> int { return GM ? tiles[(int)blockIdx.x + tl * (int)gridDim.x].nkb : nkb_conv; };
     const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-    if (tid == 0) {
-        for (int s = 0; s < TF_NW_MAX; s++) {
-            mbar_init(smem_u32(&w_full[s]), GM ? TF_NCONV : 1); mbar_init(smem_u32(&w_empty[s]), 2); mbar_init(smem_u32(&wraw_full[s]), 1);
+    if (warp == TF_WARP_ALOAD) {
+        // barriers initialised by one warp in parallel; bars[] order: w_full, w_empty, raw_full, a_full, a_empty, acc_full,
+        // acc_empty, wraw_full
+        constexpr int NB = 3 * TF_NW_MAX + 6 * TF_NA_MAX + 8;
+        for (int i = lane; i < NB; i += 32) {
+            uint32_t cnt = 1;
+            if (i < TF_NW_MAX) cnt = GM ? TF_NCONV : 1;                                          // w_full
+            else if (i < 2 * TF_NW_MAX) cnt = 2;                                                 // w_empty
+            else if (i < 2 * TF_NW_MAX + 2 * TF_NA_MAX) cnt = 1;                                 // raw_full
+            else if (i < 2 * TF_NW_MAX + 4 * TF_NA_MAX) cnt = TF_NCONV;                          // a_full
+            else if (i < 2 * TF_NW_MAX + 6 * TF_NA_MAX + 4) cnt = 1;                             // a_empty, acc_full
+            else if (i < 2 * TF_NW_MAX + 6 * TF_NA_MAX + 8) cnt = 128;                           // acc_empty
+            mbar_init(smem_u32(&bars[i]), cnt);                                                  // (rest: wraw_full, 1)
         }
-        for (int s = 0; s < 2 * TF_NA_MAX; s++) {
-            mbar_init(smem_u32(&raw_full[s]), 1); mbar_init(smem_u32(&a_full[s]), TF_NCONV); mbar_init(smem_u32(&a_empty[s]), 1);
-        }
-        for (int s = 0; s < 4; s++) { mbar_init(smem_u32(&acc_full[s]), 1); mbar_init(smem_u32(&acc_empty[s]), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
+            if (GM) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b) : "memory");
+        }
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -127,6 +138,9 @@ __global__ void __launch_bounds__(TfCfg<GM>::THREADS, 1) conv_tf_kernel(const Co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above (barriers, TMEM, tensor-map prefetch) overlapped the previous kernels' tails; from here on global
+    // memory written by them is read -- except by the weight loader of the conv form, whose bulk copies read constants
+    if (GM || warp != TF_WARP_WLOAD) pdl_wait();
 
     if (warp < 2) {
         // ===================== MMA issuer h: m-tile h of every pair tile =====================
@@ -486,7 +500,7 @@ bool try_launch_conv_tf(const ConvArgs& a, cudaStream_t st) {
         return false;
     const int tiles = L.ntiles_mp * L.ntiles_n;
     const int grid = tiles < tf_num_sms() ? tiles : tf_num_sms();
-    conv_tf_kernel<0><<<grid, TfCfg<0>::THREADS, smem, st>>>(a, L, tmx, tmx, nullptr);
+    launch_pdl(conv_tf_kernel<0>, dim3(grid), dim3(TfCfg<0>::THREADS), smem, st, a, L, tmx, tmx, nullptr);
     g_launch_count++;
     check_launch("conv_tf");
     return true;
@@ -526,7 +540,7 @@ void launch_gemm_tf(const TfGemm& g, cudaStream_t st) {
         !tensor_map_2d(&tmb, g.b, (unsigned long long)g.b_cols, (unsigned long long)g.b_rows, (unsigned long long)g.ldb, 32, (unsigned)g.nth, true))
         throw_launch_error("gemm_tf: tensor map encoding failed");
     const int grid = g.ntiles < tf_num_sms() ? g.ntiles : tf_num_sms();
-    conv_tf_kernel<1><<<grid, TfCfg<1>::THREADS, total() + 1024, st>>>(a, L, tma, tmb, g.tiles);
+    launch_pdl(conv_tf_kernel<1>, dim3(grid), dim3(TfCfg<1>::THREADS), total() + 1024, st, a, L, tma, tmb, g.tiles);
     g_launch_count++;
     check_launch("gemm_tf");
 }

@@ -27,6 +27,7 @@ __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.f + 
 // oracle: text_encoder()  x = emb[ids] * sqrt(H)
 __global__ void embed_kernel(const int* __restrict__ ids, const float* __restrict__ emb, float scale,
                              float* __restrict__ x, int rows, int H) {
+    pdl_trigger(); pdl_wait();
     const int h4 = H / 4;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)rows * h4) return;
@@ -47,6 +48,7 @@ __global__ void __launch_bounds__(256) ln_kernel(const float* __restrict__ x, co
                                                  const float* __restrict__ res2, const float* __restrict__ gamma,
                                                  const float* __restrict__ beta, float* __restrict__ out, int act,
                                                  RowMap map) {
+    pdl_trigger(); pdl_wait();
     constexpr int C = NV * 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x * 8 + warp;
@@ -89,6 +91,7 @@ __global__ void __launch_bounds__(256) dw_ln_gelu_kernel(const float* __restrict
                                                          const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float* __restrict__ out,
                                                          RowMap map) {
+    pdl_trigger(); pdl_wait();
     constexpr int C = NV * 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x * 8 + warp;
@@ -139,6 +142,7 @@ __global__ void __launch_bounds__(2 * D) attention_kernel(const float* __restric
                                                           const float* __restrict__ relv, int window,
                                                           float* __restrict__ out, int ldo, int H,
                                                           const SegInfo* __restrict__ segs, int tpad) {
+    pdl_trigger(); pdl_wait();
     const SegInfo sg = segs[blockIdx.z];
     const int T = sg.len;
     const int i0 = blockIdx.x * ATT_QT;
@@ -291,6 +295,7 @@ __global__ void __launch_bounds__(256) attn_softmax_kernel(float* __restrict__ S
                                                            float* __restrict__ orel, int ldo, int RX,
                                                            const SegInfo* __restrict__ segs,
                                                            const int* __restrict__ seg_of_gran, int gran) {
+    pdl_trigger(); pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x * 8 + warp;
     const int head = blockIdx.y;
@@ -365,6 +370,7 @@ __global__ void __launch_bounds__(256) attn_softmax_kernel(float* __restrict__ S
 __global__ void flow_pre_kernel(const float* __restrict__ z, int zcol, const float* __restrict__ w,
                                 const float* __restrict__ b, const float* __restrict__ g, float* __restrict__ h,
                                 int C, RowMap map) {
+    pdl_trigger(); pdl_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)map.rows * C) return;
     const int r = (int)(i / C), c = (int)(i % C);
@@ -377,6 +383,7 @@ __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log
 template <int NB>
 __global__ void spline_kernel(const float* __restrict__ h29, int ldh, float* __restrict__ z, int tcol,
                               float inv_sqrt_filter, RowMap map) {
+    pdl_trigger(); pdl_wait();
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= map.rows) return;
     if (!row_valid(map, r)) { z[2 * r + tcol] = 0.f; return; }
@@ -453,6 +460,7 @@ __global__ void spline_kernel(const float* __restrict__ h29, int ldh, float* __r
 
 // z[r][0..1] = eps[r][0..1] * s   (oracle: sdp_reverse  z = eps_w * noise_w)
 __global__ void scale_copy2_kernel(const float* __restrict__ eps, float s, float* __restrict__ z, RowMap map) {
+    pdl_trigger(); pdl_wait();
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= map.rows) return;
     const bool v = row_valid(map, r) && eps != nullptr;
@@ -466,6 +474,7 @@ __global__ void __launch_bounds__(256) durations_kernel(const float* __restrict_
                                                         float length_scale, const SegInfo* __restrict__ segs,
                                                         float* __restrict__ logw, int* __restrict__ cum,
                                                         int* __restrict__ y_len) {
+    pdl_trigger(); pdl_wait();
     const SegInfo sg = segs[blockIdx.x];
     __shared__ int warp_tot[8];
     __shared__ int carry_s;
@@ -506,6 +515,7 @@ __global__ void __launch_bounds__(256) expand_kernel(const float* __restrict__ s
                                                      float noise_scale, float* __restrict__ zp,
                                                      const FrameSeg* __restrict__ fsegs,
                                                      const int* __restrict__ ftile_seg, RowMap ymap) {
+    pdl_trigger(); pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x * 8 + warp;
     if (r >= ymap.rows) return;
@@ -547,6 +557,7 @@ template <int C>
 __global__ void __launch_bounds__(256) conv_post_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         float* __restrict__ wav, const FrameSeg* __restrict__ fsegs,
                                                         const int* __restrict__ ftile_seg, int U, RowMap map, int vec_ok) {
+    pdl_trigger(); pdl_wait();
     constexpr int NT = 256, ROWS = 512, LEAD = 4, SR = ROWS + 8;   // staged rows r0-4 .. r0+515
     constexpr int S = 544;                               // floats per channel row: 136 units, a multiple of 8 units >= SR/4 + 7
     extern __shared__ __align__(16) float sm[];
@@ -633,6 +644,7 @@ __device__ __forceinline__ float pcm_value(const float* __restrict__ x, long lon
 
 __global__ void i16_absmax_kernel(const float* __restrict__ wav, const FrameSeg* __restrict__ fsegs, int hop,
                                   unsigned* __restrict__ maxbits, const PcmPost post) {
+    pdl_trigger(); pdl_wait();
     const FrameSeg fs = fsegs[blockIdx.y];
     const long long n = (long long)fs.len * hop - post.trim_lo - post.trim_hi;
     const float* x = wav + fs.out_off + post.trim_lo;
@@ -646,6 +658,7 @@ __global__ void i16_absmax_kernel(const float* __restrict__ wav, const FrameSeg*
 
 __global__ void i16_convert_kernel(const float* __restrict__ wav, const FrameSeg* __restrict__ fsegs, int hop,
                                    const unsigned* __restrict__ maxbits, short* __restrict__ out, const PcmPost post) {
+    pdl_trigger(); pdl_wait();
     const FrameSeg fs = fsegs[blockIdx.y];
     const long long n = (long long)fs.len * hop - post.trim_lo - post.trim_hi;
     const float* x = wav + fs.out_off + post.trim_lo;
@@ -672,6 +685,7 @@ __device__ __forceinline__ void philox_round(unsigned& c0, unsigned& c1, unsigne
 
 __global__ void randn_kernel(float* __restrict__ out, long long n, unsigned long long seed,
                              unsigned long long stream_id) {
+    pdl_trigger(); pdl_wait();
     const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i4 * 4 >= n) return;
     unsigned c0 = (unsigned)i4, c1 = (unsigned)(i4 >> 32), c2 = (unsigned)stream_id, c3 = (unsigned)(stream_id >> 32);
@@ -698,6 +712,7 @@ __global__ void randn_kernel(float* __restrict__ out, long long n, unsigned long
 __global__ void __launch_bounds__(256) cond_bias_kernel(const float* __restrict__ w, const float* __restrict__ base,
                                                         const float* __restrict__ g, int rows, int gin,
                                                         float* __restrict__ out) {
+    pdl_trigger(); pdl_wait();
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (r >= rows) return;
     float s = 0.f;
@@ -707,6 +722,7 @@ __global__ void __launch_bounds__(256) cond_bias_kernel(const float* __restrict_
 }
 
 __global__ void fill_zero_kernel(float4* p, long long n4) {
+    pdl_trigger(); pdl_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n4) p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
@@ -721,7 +737,7 @@ void set_smem(K kern, size_t bytes) {
 // ====================================================================== launchers
 void launch_embed(const int* ids_rows, const float* emb, float scale, float* x, int rows, int H, cudaStream_t st) {
     const long long n = (long long)rows * (H / 4);
-    embed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ids_rows, emb, scale, x, rows, H);
+    launch_pdl(embed_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, ids_rows, emb, scale, x, rows, H);
     g_launch_count++;
 }
 
@@ -729,9 +745,9 @@ void launch_ln(const float* x, const float* res1, const float* res2, const float
                float* out, int C, int act, RowMap map, cudaStream_t st) {
     const unsigned grid = (map.rows + 7) / 8;
     switch (C) {
-        case 96: ln_kernel<3><<<grid, 256, 0, st>>>(x, res1, res2, gamma, beta, out, act, map); break;
-        case 192: ln_kernel<6><<<grid, 256, 0, st>>>(x, res1, res2, gamma, beta, out, act, map); break;
-        case 256: ln_kernel<8><<<grid, 256, 0, st>>>(x, res1, res2, gamma, beta, out, act, map); break;
+        case 96: launch_pdl(ln_kernel<3>, dim3(grid), dim3(256), 0, st, x, res1, res2, gamma, beta, out, act, map); break;
+        case 192: launch_pdl(ln_kernel<6>, dim3(grid), dim3(256), 0, st, x, res1, res2, gamma, beta, out, act, map); break;
+        case 256: launch_pdl(ln_kernel<8>, dim3(grid), dim3(256), 0, st, x, res1, res2, gamma, beta, out, act, map); break;
         default: throw_launch_error("LayerNorm: unsupported channel count (96 / 192 / 256)");
     }
     g_launch_count++;
@@ -741,9 +757,9 @@ void launch_dw_ln_gelu(const float* x, const float* wdw, const float* bdw, int k
                        const float* beta, float* out, int C, RowMap map, cudaStream_t st) {
     const unsigned grid = (map.rows + 7) / 8;
     switch (C) {
-        case 96: dw_ln_gelu_kernel<3><<<grid, 256, 0, st>>>(x, wdw, bdw, k, dil, gamma, beta, out, map); break;
-        case 192: dw_ln_gelu_kernel<6><<<grid, 256, 0, st>>>(x, wdw, bdw, k, dil, gamma, beta, out, map); break;
-        case 256: dw_ln_gelu_kernel<8><<<grid, 256, 0, st>>>(x, wdw, bdw, k, dil, gamma, beta, out, map); break;
+        case 96: launch_pdl(dw_ln_gelu_kernel<3>, dim3(grid), dim3(256), 0, st, x, wdw, bdw, k, dil, gamma, beta, out, map); break;
+        case 192: launch_pdl(dw_ln_gelu_kernel<6>, dim3(grid), dim3(256), 0, st, x, wdw, bdw, k, dil, gamma, beta, out, map); break;
+        case 256: launch_pdl(dw_ln_gelu_kernel<8>, dim3(grid), dim3(256), 0, st, x, wdw, bdw, k, dil, gamma, beta, out, map); break;
         default: throw_launch_error("DDSConv: unsupported channel count (96 / 192 / 256)");
     }
     g_launch_count++;
@@ -764,10 +780,10 @@ void launch_attention(const float* qkv, int ldq, const float* relk, const float*
     dim3 grid((max_len + ATT_QT - 1) / ATT_QT, heads, nseg);
     if (D == 96) {
         set_smem(attention_kernel<96>, smem);
-        attention_kernel<96><<<grid, 192, smem, st>>>(qkv, ldq, relk, relv, window, out, ldo, H, segs, tpad);
+        launch_pdl(attention_kernel<96>, dim3(grid), dim3(192), smem, st, qkv, ldq, relk, relv, window, out, ldo, H, segs, tpad);
     } else if (D == 48) {
         set_smem(attention_kernel<48>, smem);
-        attention_kernel<48><<<grid, 96, smem, st>>>(qkv, ldq, relk, relv, window, out, ldo, H, segs, tpad);
+        launch_pdl(attention_kernel<48>, dim3(grid), dim3(96), smem, st, qkv, ldq, relk, relv, window, out, ldo, H, segs, tpad);
     } else throw_launch_error("attention: unsupported head size (96 / 48)");
     g_launch_count++;
 }
@@ -779,41 +795,40 @@ void launch_attn_softmax(float* S, int Tp, const float* qkv, int ldq, const floa
     dim3 grid((RX + 7) / 8, heads);
     if (D != 96 || max_len > 1280 || 2 * window + 1 > 32) throw_launch_error("attn_softmax: unsupported head size / length");
     if (max_len <= 640)
-        attn_softmax_kernel<96, 20><<<grid, 256, 0, st>>>(S, Tp, qkv, ldq, relk, relv, window, orel, ldo, RX, segs, seg_of_gran, gran);
+        launch_pdl(attn_softmax_kernel<96, 20>, dim3(grid), dim3(256), 0, st, S, Tp, qkv, ldq, relk, relv, window, orel, ldo, RX, segs, seg_of_gran, gran);
     else
-        attn_softmax_kernel<96, 40><<<grid, 256, 0, st>>>(S, Tp, qkv, ldq, relk, relv, window, orel, ldo, RX, segs, seg_of_gran, gran);
+        launch_pdl(attn_softmax_kernel<96, 40>, dim3(grid), dim3(256), 0, st, S, Tp, qkv, ldq, relk, relv, window, orel, ldo, RX, segs, seg_of_gran, gran);
     g_launch_count++;
 }
 
 void launch_flow_pre(const float* z, int zcol, const float* w, const float* b, const float* g, float* h, int C,
                      RowMap map, cudaStream_t st) {
     const long long n = (long long)map.rows * C;
-    flow_pre_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(z, zcol, w, b, g, h, C, map);
+    launch_pdl(flow_pre_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, z, zcol, w, b, g, h, C, map);
     g_launch_count++;
 }
 
 void launch_spline(const float* h29, int ldh, float* z, int tcol, int bins, float inv_sqrt_filter, RowMap map,
                    cudaStream_t st) {
     (void)bins;   // 10 bins is the only configuration Piper ships
-    spline_kernel<10><<<(map.rows + 127) / 128, 128, 0, st>>>(h29, ldh, z, tcol, inv_sqrt_filter, map);
+    launch_pdl(spline_kernel<10>, dim3((map.rows + 127) / 128), dim3(128), 0, st, h29, ldh, z, tcol, inv_sqrt_filter, map);
     g_launch_count++;
 }
 
 void launch_scale_copy2(const float* eps, float s, float* z, RowMap map, cudaStream_t st) {
-    scale_copy2_kernel<<<(map.rows + 255) / 256, 256, 0, st>>>(eps, s, z, map);
+    launch_pdl(scale_copy2_kernel, dim3((map.rows + 255) / 256), dim3(256), 0, st, eps, s, z, map);
     g_launch_count++;
 }
 
 void launch_durations(const float* z, float m0, float logs0, float length_scale, const SegInfo* segs, int nseg,
                       float* logw, int* cum, int* y_len, cudaStream_t st) {
-    durations_kernel<<<nseg, 256, 0, st>>>(z, m0, logs0, length_scale, segs, logw, cum, y_len);
+    launch_pdl(durations_kernel, dim3(nseg), dim3(256), 0, st, z, m0, logs0, length_scale, segs, logw, cum, y_len);
     g_launch_count++;
 }
 
 void launch_expand(const float* stats, int ldst, int I, const int* cum, const float* eps, float noise_scale,
                    float* zp, const FrameSeg* fsegs, const int* ftile_seg, RowMap ymap, cudaStream_t st) {
-    expand_kernel<<<(ymap.rows + 7) / 8, 256, 0, st>>>(stats, ldst, I, cum, eps, noise_scale, zp, fsegs, ftile_seg,
-                                                       ymap);
+    launch_pdl(expand_kernel, dim3((ymap.rows + 7) / 8), dim3(256), 0, st, stats, ldst, I, cum, eps, noise_scale, zp, fsegs, ftile_seg, ymap);
     g_launch_count++;
 }
 
@@ -824,9 +839,9 @@ void launch_conv_post(const float* x, int C, const float* w, float* wav, const F
     const size_t smem = sizeof(float) * ((size_t)C * 544 + (size_t)C * 8);
     const int vec_ok = (reinterpret_cast<uintptr_t>(wav) & 15) == 0;     // out_off is a multiple of U samples
     switch (C) {
-        case 16: set_smem(conv_post_kernel<16>, smem); conv_post_kernel<16><<<grid, 256, smem, st>>>(x, w, wav, fsegs, ftile_seg, U, map, vec_ok); break;
-        case 32: set_smem(conv_post_kernel<32>, smem); conv_post_kernel<32><<<grid, 256, smem, st>>>(x, w, wav, fsegs, ftile_seg, U, map, vec_ok); break;
-        case 64: set_smem(conv_post_kernel<64>, smem); conv_post_kernel<64><<<grid, 256, smem, st>>>(x, w, wav, fsegs, ftile_seg, U, map, vec_ok); break;
+        case 16: set_smem(conv_post_kernel<16>, smem); launch_pdl(conv_post_kernel<16>, dim3(grid), dim3(256), smem, st, x, w, wav, fsegs, ftile_seg, U, map, vec_ok); break;
+        case 32: set_smem(conv_post_kernel<32>, smem); launch_pdl(conv_post_kernel<32>, dim3(grid), dim3(256), smem, st, x, w, wav, fsegs, ftile_seg, U, map, vec_ok); break;
+        case 64: set_smem(conv_post_kernel<64>, smem); launch_pdl(conv_post_kernel<64>, dim3(grid), dim3(256), smem, st, x, w, wav, fsegs, ftile_seg, U, map, vec_ok); break;
         default: throw_launch_error("conv_post: unsupported channel count (16 / 32 / 64)");
     }
     g_launch_count++;
@@ -840,25 +855,25 @@ void launch_i16(const float* wav, const FrameSeg* fsegs, int nseg, int hop, long
     if (bx < 1) bx = 1;
     if (bx > 1024) bx = 1024;
     dim3 grid(bx, nseg);
-    i16_absmax_kernel<<<grid, 256, 0, st>>>(wav, fsegs, hop, maxbits, post);
-    i16_convert_kernel<<<grid, 256, 0, st>>>(wav, fsegs, hop, maxbits, out, post);
+    launch_pdl(i16_absmax_kernel, dim3(grid), dim3(256), 0, st, wav, fsegs, hop, maxbits, post);
+    launch_pdl(i16_convert_kernel, dim3(grid), dim3(256), 0, st, wav, fsegs, hop, maxbits, out, post);
     g_launch_count += 2;
 }
 
 void launch_randn(float* out, long long n, unsigned long long seed, unsigned long long stream_id, cudaStream_t st) {
     const long long n4 = (n + 3) / 4;
-    randn_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(out, n, seed, stream_id);
+    launch_pdl(randn_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st, out, n, seed, stream_id);
     g_launch_count++;
 }
 
 void launch_cond_bias(const float* w, const float* base, const float* g, int rows, int gin, float* out, cudaStream_t st) {
-    cond_bias_kernel<<<(rows + 7) / 8, 256, 0, st>>>(w, base, g, rows, gin, out);
+    launch_pdl(cond_bias_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, w, base, g, rows, gin, out);
     g_launch_count++;
 }
 
 void launch_fill_zero(float* p, long long n, cudaStream_t st) {
     const long long n4 = n / 4;
-    fill_zero_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<float4*>(p), n4);
+    launch_pdl(fill_zero_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st, reinterpret_cast<float4*>(p), n4);
     g_launch_count++;
 }
 
