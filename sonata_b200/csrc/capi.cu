@@ -9,9 +9,17 @@
 
 using namespace sb200;
 
-struct sb200_voice { Voice* v; };
-struct sb200_job { Job* j; };
-struct sb200_latent { Latent* l; };
+// Handles.  A job returns its context to the voice's pool when it dies and a latent belongs to a voice, so both share
+// ownership of the voice: freeing the voice handle first (garbage-collected callers free in any order) is safe.
+struct sb200_voice { std::shared_ptr<Voice> v; };
+struct sb200_job {
+    Job* j; std::shared_ptr<Voice> keep;
+    ~sb200_job() { delete j; }
+};
+struct sb200_latent {
+    Latent* l; std::shared_ptr<Voice> keep;
+    ~sb200_latent() { delete l; }
+};
 
 namespace {
 
@@ -127,10 +135,10 @@ int32_t sb200_voice_load(const char* config_path, int32_t device, sb200_voice** 
     return guarded(err, [&] {
         if (!config_path || !out) throw Error(19, "null argument");
         Voice* v = load_voice(config_path, device);
-        *out = new sb200_voice{v};
+        *out = new sb200_voice{std::shared_ptr<Voice>(v)};
     });
 }
-void sb200_voice_free(sb200_voice* v) { if (v) { delete v->v; delete v; } }
+void sb200_voice_free(sb200_voice* v) { delete v; }
 
 int32_t sb200_audio_output_info(const sb200_voice* v, sb200_audio_info* out, sb200_error* err) {
     return guarded(err, [&] {
@@ -189,7 +197,7 @@ int32_t sb200_speak_batch_ids(sb200_voice* v, const int64_t* ids, const size_t* 
     return guarded(err, [&] {
         const double t0 = now_ms();
         static_assert(sizeof(long long) == sizeof(int64_t), "");
-        std::unique_ptr<Job> j(create_job(v->v, reinterpret_cast<const long long*>(ids), offsets, batch, nullptr,
+        std::unique_ptr<Job> j(create_job(v->v.get(), reinterpret_cast<const long long*>(ids), offsets, batch, nullptr,
                                           nullptr, nullptr, false));
         j->run(nullptr, 0);
         fetch_audio(*j, outs, 0.f);
@@ -223,8 +231,8 @@ int32_t sb200_job_create(sb200_voice* v, const int64_t* ids, const size_t* offse
                          const float* const* eps_w, const float* const* eps_z, const size_t* eps_z_frames,
                          sb200_job** out, sb200_error* err) {
     return guarded(err, [&] {
-        Job* j = create_job(v->v, reinterpret_cast<const long long*>(ids), offsets, batch, eps_w, eps_z, eps_z_frames, false);
-        *out = new sb200_job{j};
+        Job* j = create_job(v->v.get(), reinterpret_cast<const long long*>(ids), offsets, batch, eps_w, eps_z, eps_z_frames, false);
+        *out = new sb200_job{j, v->v};
     });
 }
 int32_t sb200_job_set_debug(sb200_job* job, int32_t on) { job->j->debug = on != 0; return 0; }
@@ -319,23 +327,23 @@ int32_t sb200_job_lengths(const sb200_job* job, int64_t* frames, int64_t* sample
     }
     return 0;
 }
-void sb200_job_free(sb200_job* job) { if (job) { delete job->j; delete job; } }
+void sb200_job_free(sb200_job* job) { delete job; }
 
 // ---- streaming halves ----
 int32_t sb200_encode_ids(sb200_voice* v, const int64_t* ids, size_t n, sb200_latent** out, sb200_error* err) {
-    return guarded(err, [&] { *out = new sb200_latent{encode_latent(v->v, reinterpret_cast<const long long*>(ids), n)}; });
+    return guarded(err, [&] { *out = new sb200_latent{encode_latent(v->v.get(), reinterpret_cast<const long long*>(ids), n), v->v}; });
 }
 int64_t sb200_latent_frames(const sb200_latent* z) { return z->l->frames; }
 int32_t sb200_decode_chunk(sb200_voice* v, const sb200_latent* z, int64_t lo, int64_t hi, sb200_audio* out, sb200_error* err) {
     return guarded(err, [&] {
         std::vector<float> w; float ms = 0;
-        decode_latent_chunk(v->v, z->l, lo, hi, w, &ms);
+        decode_latent_chunk(v->v.get(), z->l, lo, hi, w, &ms);
         out->data = (float*)malloc(w.size() * 4 + 4);
         memcpy(out->data, w.data(), w.size() * 4);
         out->len = w.size(); out->inference_ms = ms; out->sample_rate = (uint32_t)v->v->sample_rate;
     });
 }
-void sb200_latent_free(sb200_latent* z) { if (z) { delete z->l; delete z; } }
+void sb200_latent_free(sb200_latent* z) { delete z; }
 
 // ---- introspection ----
 int32_t sb200_job_debug_fetch(sb200_job* job, const char* name, size_t b, float** data, size_t* rows, size_t* cols, sb200_error* err) {

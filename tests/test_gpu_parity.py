@@ -295,6 +295,7 @@ def test_full_size_properties(models):
         assert np.isfinite(s).all() and np.abs(s).max() <= 1.0
     # utterance 5 of the big batch == the same utterance alone (batch-size independence)
     alone = m.infer_with_values(batches[5]).samples.as_slice()
+    assert alone.shape == auds[5].samples.as_slice().shape
     assert float(np.abs(alone - auds[5].samples.as_slice()).max()) < 1e-5
     prof = {p["name"]: p for p in job.profile()}
     assert prof["dec.mrf2"]["launches"] == 6 and prof["dec.mrf2"]["ms"] > 0
@@ -370,3 +371,18 @@ def test_concurrent_calls_are_reentrant(models):
 def test_smoke_entry():
     import __graft_entry__ as ge
     ge.smoke()
+
+
+def test_handles_may_be_freed_in_any_order(voice_paths):
+    """A job hands its context back to the voice's pool and a latent belongs to a voice: both share ownership of the
+    voice, so a garbage-collected caller that drops the model first does not touch freed memory (seen as
+    `std::system_error: Invalid argument` from the pool mutex at interpreter exit)."""
+    m = sonata_b200.from_config_path(voice_paths["medium"], device=0)
+    _det(m)
+    ids = workload.synthetic_ids(64, utt=3)
+    job = SynthesisJob(m, [ids]); job.run()
+    n = job.lengths()[1][0]
+    m.close()                                     # voice handle first ...
+    out = job.fetch()[0].samples.as_slice()       # ... the job still owns the weights it reads
+    assert out.shape[0] == n and np.isfinite(out).all()
+    job.close()

@@ -92,7 +92,8 @@ CASES = [
 # layers): fp32-class accuracy is the point, so these cases are held to TF_TOL against the fp64 reference (the fp32
 # FMA chain of backend 0 measures 2e-6 .. 1e-5 on the same cases).  Shapes: every (cin, cout, k) of the encoder and
 # the duration predictor, all three column tiles (96 / 64 / 32), ragged row counts (odd number of 128-row tiles in
-# the last pair), residual / scale / accumulate / masked rows, a leaky-ReLU prologue, and multi-tile persistent runs.
+# the last pair), residual / scale / accumulate / masked rows, a leaky-ReLU prologue, multi-tile persistent runs, and the
+# single-utterance shapes (a handful of tiles with a long K loop).
 TF_TOL = 1.5e-5
 TF_CASES = [
     (256, 192, 576, 1, 1, 1.0, 0, False, 1.0, False, None),
@@ -105,6 +106,8 @@ TF_CASES = [
     (640, 64, 64, 3, 1, 1.0, 0, True, 1.0, False, 600),
     (384, 96, 128, 5, 2, 0.1, 0, False, 1.0, False, 380),
     (128, 32, 32, 1, 1, 1.0, 0, False, 1.0, False, 100),
+    (256, 416, 64, 3, 1, 1.0, 0, True, 1.0, False, 250),       # odd K-block count, two tiles
+    (512, 768, 192, 3, 1, 1.0, 1, False, 1.0, False, 258),      # the single-utterance ffn2 shape (72 stages on 4 CTAs)
     (148 * 256 * 2 + 300, 192, 192, 3, 1, 1.0, 0, False, 1.0, False, 148 * 256 * 2 + 17),
     (18432, 192, 576, 1, 1, 1.0, 0, False, 1.0, False, 18000),
     (18432, 768, 192, 3, 1, 1.0, 0, True, 1.0, False, None),
