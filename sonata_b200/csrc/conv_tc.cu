@@ -70,6 +70,7 @@ struct TcLaunch {
     int depth;       // window loads in flight per pipeline (< na: see plan())
     int v8;          // every epilogue operand is 32-byte aligned: 256-bit global accesses
     int tma_st;      // MODE 2: output tile leaves through a TMA tensor store
+    int nstg;        // MODE 2: staging tiles per pipeline (1 = residual-in / output, 2 = + previous value of an accumulated buffer)
     // "cat" mode (nt <= 64, resident weights): the weight image of a tap stacks the hi rows and the lo rows along N,
     // so  A_hi x [W_hi ; W_lo]  is ONE MMA of N = 2*nt (columns [0,nt) = hi*hi, [nt,2nt) = hi*lo) and  A_lo x W_hi
     // accumulates into the first nt columns: 2 MMAs instead of 3 per (tap, K-step).  One thread can issue an
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
     uint8_t* A0 = smem;                                         // [2][na] stages
     uint8_t* W0 = A0 + (size_t)2 * L.na * a_buf;                // resident: [ws]; ring: [2][ws]
     uint8_t* EX = W0 + (size_t)wslots * w_stage;                // MODE 2: [2 pipelines][2] staging tiles
-    uint64_t* bars = reinterpret_cast<uint64_t*>(EX + (MODE == 2 ? 4 * TC_OUT_BYTES : 0));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(EX + (MODE == 2 ? 2 * L.nstg * TC_OUT_BYTES : 0));
     uint64_t* w_full = bars;                               // [TC_MAX_WRING]
     uint64_t* w_empty = w_full + TC_MAX_WRING;             // [TC_MAX_WRING]
     uint64_t* a_full = w_empty + TC_MAX_WRING;             // [2][TC_MAX_ASTAGES]
@@ -164,6 +165,29 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
     // memory written by them is read -- except by the weight warps, whose bulk copies read constants (their TMA-agent
     // part waits before its first fetch)
     if (warp != 2 && warp != 3) pdl_wait();
+
+    // MODE 2 staging traffic (used by the TMA-agent warps, or by the epilogue groups themselves when the weight warps
+    // are busy streaming)
+    const int nch = L.nt / 32;                       // MODE 2: 32-column chunks per tile, one staged item each
+    // MODE 2 item `it` of pipeline pp: tile pp + 2 * (it / nch), chunk it % nch
+    auto item_row = [&](int pp, int it) { return ((int)blockIdx.x + (pp + 2 * (it / nch)) * (int)gridDim.x) / L.ntiles_n * 128; };
+    auto agent_fetch = [&](int pp, int it) {
+        const uint32_t st = smem_u32(EX + (size_t)pp * L.nstg * TC_OUT_BYTES);     // [0] residual-in / output, [1] previous
+        const uint32_t bytes = (a.res ? TC_OUT_BYTES : 0) + (a.acc0 ? TC_OUT_BYTES : 0);
+        // nothing to fetch: still publish "staging tile free" (the previous store has been read out)
+        if (!bytes) { mbar_arrive(smem_u32(&epi_full[pp])); return; }
+        const int r0 = item_row(pp, it), c0 = (it % nch) * 32;
+        mbar_expect_tx(smem_u32(&epi_full[pp]), bytes);
+        if (a.res) tma_load_2d(st, &tm_res, smem_u32(&epi_full[pp]), c0, r0);
+        if (a.acc0) tma_load_2d(st + TC_OUT_BYTES, &tm_out, smem_u32(&epi_full[pp]), c0, r0);
+    };
+    auto agent_store = [&](int pp, int it) {
+        const uint32_t st = smem_u32(EX + (size_t)pp * L.nstg * TC_OUT_BYTES);
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                     ::"l"(&tm_out), "r"(st), "r"((it % nch) * 32), "r"(item_row(pp, it)) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    };
 
     if (warp < 2) {
         // ===================== MMA issuer of pipeline p = warp =====================
@@ -239,6 +263,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
     } else if (warp < 4) {
         // ===================== weight producer of pipeline p = warp - 2 =====================
         const int p = warp - 2;
+        {
         if (lane == 0) {
             if (L.resident) {
                 if (p == 0) {
@@ -266,34 +291,23 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                 }
             }
         }
-        if constexpr (MODE == 2) {
+        if (MODE == 2 && L.resident) {
             // ---- TMA agent of pipeline p (the weight warps are idle once the resident weights are in): stores the
-            // staged output tile, waits until the engine has read it, then fetches the residual / previous-value
-            // tiles of the pipeline's next tile into the same staging buffers.  The epilogue threads never wait for
+            // staged output chunk, waits until the engine has read it, then fetches the residual / previous-value
+            // chunk of the pipeline's next item into the same staging buffers.  The epilogue threads never wait for
             // a store and never touch global memory.
             if (lane == 0) {
                 pdl_wait();                                                           // residual / previous tiles: predecessor data
-                const uint32_t st = smem_u32(EX + (size_t)p * 2 * TC_OUT_BYTES);      // [0] residual-in / output, [1] previous
-                const uint32_t bytes = (a.res ? TC_OUT_BYTES : 0) + (a.acc0 ? TC_OUT_BYTES : 0);
-                auto fetch = [&](int tl) {
-                    // nothing to fetch: still publish "staging tile free" (the previous store has been read out)
-                    if (!bytes) { mbar_arrive(smem_u32(&epi_full[p])); return; }
-                    const int r0 = ((int)blockIdx.x + tl * (int)gridDim.x) * 128;
-                    mbar_expect_tx(smem_u32(&epi_full[p]), bytes);
-                    if (a.res) tma_load_2d(st, &tm_res, smem_u32(&epi_full[p]), 0, r0);
-                    if (a.acc0) tma_load_2d(st + TC_OUT_BYTES, &tm_out, smem_u32(&epi_full[p]), 0, r0);
-                };
-                if (p < my_tiles) fetch(p);
-                for (int tl = p, lt = 0; tl < my_tiles; tl += 2, lt++) {
-                    mbar_wait(smem_u32(&staged[p]), (uint32_t)(lt & 1));
-                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                                 ::"l"(&tm_out), "r"(st), "r"(0), "r"(((int)blockIdx.x + tl * (int)gridDim.x) * 128) : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    if (tl + 2 < my_tiles) fetch(tl + 2);
+                const int nitems = ((my_tiles - p + 1) / 2) * nch;
+                if (nitems) agent_fetch(p, 0);
+                for (int it = 0; it < nitems; it++) {
+                    mbar_wait(smem_u32(&staged[p]), (uint32_t)(it & 1));
+                    agent_store(p, it);
+                    if (it + 1 < nitems) agent_fetch(p, it + 1);
                 }
                 asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before the CTA retires
             }
+        }
         }
         __syncwarp();
     } else if (warp < TC_EPI0) {
@@ -425,60 +439,76 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
             // A row-per-thread LDG/STG touches 32 different lines per instruction (one L1TEX data-pipe wavefront
             // per thread); ncu showed that pipe 83 % busy, two thirds of it global wavefronts, while HBM and L2
             // sat at 40 %.
-            const uint32_t st = smem_u32(EX + (size_t)p * 2 * TC_OUT_BYTES) + (uint32_t)row * 128u;
+            const uint32_t st = smem_u32(EX + (size_t)p * L.nstg * TC_OUT_BYTES) + (uint32_t)row * 128u;
             const uint32_t sw = (uint32_t)(row & 7);
+            int it = 0;
+            // streamed weights keep warps 2 / 3 busy: the epilogue group is its own TMA agent (thread 0 stores the chunk
+            // once the group's 128 threads have staged it, and fetches the next operands into the same buffers)
+            const bool self = !L.resident;
+            const int nitems = ((my_tiles - p + 1) / 2) * nch;
+            if (self && row == 0 && nitems) agent_fetch(p, 0);
             for (int tl = p, lt = 0; tl < my_tiles; tl += 2, lt++) {
                 const int tg = (int)blockIdx.x + tl * (int)gridDim.x;
-                const int q = tg * 128 + row;
+                const int q = (tg / L.ntiles_n) * 128 + row;
                 const int acc = p + 2 * (lt & 1);
                 const bool valid = q < a.rows_q && row_valid(a.map, q);
                 mbar_wait(smem_u32(&acc_full[acc]), (uint32_t)((lt >> 1) & 1));
                 tc_fence_after();
                 if (p == 0 && warp == TC_EPI0 && lane == 0) TC_TRACE(a, lt, 5);
-                float o[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * L.accw), o);
-                if (L.cat) {                  // second column half: the hi*lo products
-                    float t[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * L.accw + 32), t);
+                for (int ch = 0; ch < nch; ch++, it++) {
+                    float o[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * L.accw + ch * 32), o);
+                    if (L.cat) {                  // second column half: the hi*lo products
+                        float t[32];
+                        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * L.accw + L.nt + ch * 32), t);
 #pragma unroll
-                    for (int j = 0; j < 32; j++) o[j] += t[j];
-                }
-                tc_fence_before();
-                mbar_arrive(smem_u32(&acc_empty[acc]));
-                if (p == 0 && warp == TC_EPI0 && lane == 0) TC_TRACE(a, lt, 6);
-                if (a.bias) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b = *reinterpret_cast<const float4*>(a.bias + j);
-                        o[j] += b.x; o[j + 1] += b.y; o[j + 2] += b.z; o[j + 3] += b.w;
+                        for (int j = 0; j < 32; j++) o[j] += t[j];
                     }
-                }
-                if (a.act == ACT_RELU) {
+                    if (ch == nch - 1) {          // accumulator fully read: hand it back to its MMA warp
+                        tc_fence_before();
+                        mbar_arrive(smem_u32(&acc_empty[acc]));
+                        if (p == 0 && warp == TC_EPI0 && lane == 0) TC_TRACE(a, lt, 6);
+                    }
+                    if (a.bias) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) o[j] = fmaxf(o[j], 0.f);
-                }
-                mbar_wait(smem_u32(&epi_full[p]), (uint32_t)(lt & 1));     // operands landed AND staging tile free
-                // gap rows are written as zeros (accumulated buffers hold zeros there already); rows past the end of
-                // the array are clipped by the tensor map
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b = *reinterpret_cast<const float4*>(a.bias + ch * 32 + j);
+                            o[j] += b.x; o[j + 1] += b.y; o[j + 2] += b.z; o[j + 3] += b.w;
+                        }
+                    }
+                    if (a.act == ACT_RELU) {
 #pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    const uint32_t off = (((uint32_t)c ^ sw) << 4);
-                    float4 r = make_float4(0.f, 0.f, 0.f, 0.f), pv = r;
-                    if (a.res) r = lds128(st + off);
-                    if (a.acc0) pv = lds128(st + TC_OUT_BYTES + off);
-                    uint4 u;
-                    u.x = __float_as_uint(valid ? fmaf(o[4 * c] + r.x, a.scale, pv.x) : 0.f);
-                    u.y = __float_as_uint(valid ? fmaf(o[4 * c + 1] + r.y, a.scale, pv.y) : 0.f);
-                    u.z = __float_as_uint(valid ? fmaf(o[4 * c + 2] + r.z, a.scale, pv.z) : 0.f);
-                    u.w = __float_as_uint(valid ? fmaf(o[4 * c + 3] + r.w, a.scale, pv.w) : 0.f);
-                    sts128u(st + off, u);
+                        for (int j = 0; j < 32; j++) o[j] = fmaxf(o[j], 0.f);
+                    }
+                    mbar_wait(smem_u32(&epi_full[p]), (uint32_t)(it & 1));     // operands landed AND staging tile free
+                    // gap rows are written as zeros (accumulated buffers hold zeros there already); rows past the end of
+                    // the array are clipped by the tensor map
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                        const uint32_t off = (((uint32_t)c ^ sw) << 4);
+                        float4 r = make_float4(0.f, 0.f, 0.f, 0.f), pv = r;
+                        if (a.res) r = lds128(st + off);
+                        if (a.acc0) pv = lds128(st + TC_OUT_BYTES + off);
+                        uint4 u;
+                        u.x = __float_as_uint(valid ? fmaf(o[4 * c] + r.x, a.scale, pv.x) : 0.f);
+                        u.y = __float_as_uint(valid ? fmaf(o[4 * c + 1] + r.y, a.scale, pv.y) : 0.f);
+                        u.z = __float_as_uint(valid ? fmaf(o[4 * c + 2] + r.z, a.scale, pv.z) : 0.f);
+                        u.w = __float_as_uint(valid ? fmaf(o[4 * c + 3] + r.w, a.scale, pv.w) : 0.f);
+                        sts128u(st + off, u);
+                    }
+                    fence_async_smem();                                  // generic-proxy stores -> visible to the TMA engine
+                    if (self) {
+                        asm volatile("bar.sync %0, 128;" ::"r"(1 + p) : "memory");
+                        if (row == 0) {
+                            agent_store(p, it);
+                            if (it + 1 < nitems) agent_fetch(p, it + 1);
+                        }
+                    } else mbar_arrive(smem_u32(&staged[p]));
                 }
-                fence_async_smem();                                  // generic-proxy stores -> visible to the TMA engine
-                mbar_arrive(smem_u32(&staged[p]));
                 if (p == 0 && warp == TC_EPI0 && lane == 0) TC_TRACE(a, lt, 7);
             }
+            if (self && row == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before the CTA retires
         } else {
-        const int nch = L.nt / 32;
         const bool gate = a.act == ACT_GATE;
         for (int tl = p, lt = 0; tl < my_tiles; tl += 2, lt++) {
             const int tg = (int)blockIdx.x + tl * (int)gridDim.x;
@@ -601,9 +631,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
     }
 }
 
-// [rows][32] fp32 view of an output buffer: 128 x 32 boxes, SWIZZLE_128B in shared memory
-bool make_out_map(CUtensorMap* tm, float* base, int rows, int ld) {
-    return tensor_map_2d(tm, base, 32, (unsigned long long)rows, (unsigned long long)ld, 32, 128, true);
+// [rows][cols] fp32 view of an output buffer: 128-row x 32-column boxes, SWIZZLE_128B in shared memory
+bool make_out_map(CUtensorMap* tm, float* base, int cols, int rows, int ld) {
+    return tensor_map_2d(tm, base, (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)ld, 32, 128, true);
 }
 
 // [rows][cin] fp32 view of a conv input: boxes of 32 channels x win rows, linear (unswizzled) in shared memory --
@@ -622,13 +652,19 @@ bool epi_v8_ok(const ConvArgs& a) {
     return al(a.res, a.ldres) && al(a.y0, a.ldy0) && al(a.y1, a.ldy1);
 }
 
-bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem) {
+bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem, bool allow_tma_st = true) {
     if (!a.wtc || a.tc_nt <= 0 || a.tc_nt > 128) return false;
     L.nt = a.tc_nt;
     L.v8 = epi_v8_ok(a) ? 1 : 0;
-    L.tma_st = (L.v8 && a.cout == 32 && L.nt == 32 && a.act != ACT_GATE && !a.phase_cols && a.split >= a.cout && a.orow_mul == 1 &&
-                tensor_map_encoder() != nullptr && !SB_ENV_ONCE("SB200_TC_NOTMAST")) ? 1 : 0;
+    // TMA-staged epilogue: one output buffer, plain row mapping, whole 32-column chunks (32 / 64 / 128 output channels in
+    // ONE column tile).  SB200_TC_TMAST_MAXC caps the channel count (A/B against the row-per-thread epilogue).
+    int tmast_maxc = 64;
+    { const char* e = SB_ENV_ONCE("SB200_TC_TMAST_MAXC"); if (e) tmast_maxc = atoi(e); }
+    L.tma_st = (allow_tma_st && L.v8 && (a.cout == 32 || a.cout == 64 || a.cout == 128) && a.cout <= tmast_maxc && L.nt == a.cout &&
+                a.act != ACT_GATE && !a.phase_cols && a.split >= a.cout && a.orow_mul == 1 && tensor_map_encoder() != nullptr &&
+                !SB_ENV_ONCE("SB200_TC_NOTMAST")) ? 1 : 0;
     if (a.res && (a.ldres & 3)) L.tma_st = 0;
+    L.nstg = a.acc0 ? 2 : 1;
     L.win = (128 + a.span + 7) & ~7;
     if (L.win * 4 > TC_MAXCH * TC_GROUP) return false;
     L.cat = 0; L.accw = L.nt; L.idesc2 = 0;
@@ -640,11 +676,12 @@ bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem) {
     const size_t w_stage = (size_t)L.nt * 128;
     const int per_tile = (a.cin / 32) * a.ntaps;
     const size_t budget = 225 * 1024 - 2048;
-    const size_t bar_bytes = (2 * TC_MAX_WRING + 6 * TC_MAX_ASTAGES + 12) * 8 + 16 + (L.tma_st ? 4 * TC_OUT_BYTES : 0);
+    const size_t bar_bytes = (2 * TC_MAX_WRING + 6 * TC_MAX_ASTAGES + 12) * 8 + 16 + (L.tma_st ? 2 * L.nstg * TC_OUT_BYTES : 0);
     L.bulk_in = (SB_ENV_ONCE("SB200_TC_NOBULKIN") == nullptr && a.ldx == 32 && a.cin == 32) ? 1 : 0;
     L.tma_in = (tensor_map_encoder() != nullptr && L.win <= 256 && (a.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0 &&
                 !SB_ENV_ONCE("SB200_TC_NOTMAIN")) ? 1 : 0;
     L.resident = (L.ntiles_n == 1 && per_tile <= TC_MAX_WRING && per_tile * w_stage + 4 * a_buf + bar_bytes <= budget) ? 1 : 0;
+    if (L.tma_st && !L.resident && SB_ENV_ONCE("SB200_TC_TMAST_RESONLY")) return plan(a, L, smem, false);
     const int wper_cat = (a.cin / 32) * ((a.ntaps + 1) / 2);
     if (a.wcat && L.tma_st && L.nt <= 64 && L.resident && wper_cat * 2 * w_stage + 4 * a_buf + bar_bytes <= budget && !SB_ENV_ONCE("SB200_TC_NOCAT")) {
         L.cat = 1; L.accw = 2 * L.nt;
@@ -746,12 +783,18 @@ bool try_launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     v = a;
     if (L.cat) v.wtc = a.wcat;
     if (L.tma_in && !make_in_map(&tmx, a.x, a.rows_in, a.cin, a.ldx, L.win)) L.tma_in = 0;
-    if (L.tma_st && L.resident && make_out_map(&tm, a.y0 + (size_t)a.orow_add * a.ldy0, a.rows_q, a.ldy0) &&
-        (!a.res || make_out_map(&tmr, const_cast<float*>(a.res) + (size_t)a.orow_add * a.ldres, a.rows_q, a.ldres))) {
-        launch_pdl(conv_tc_kernel<2>, dim3(grid), dim3(TC2_THREADS), smem, st, v, L, tm, tmr, tmx);
-        g_launch_count++;
-        check_launch("conv_tc_tma");
-        return true;
+    if (L.tma_st) {
+        if (make_out_map(&tm, a.y0 + (size_t)a.orow_add * a.ldy0, a.cout, a.rows_q, a.ldy0) &&
+            (!a.res || make_out_map(&tmr, const_cast<float*>(a.res) + (size_t)a.orow_add * a.ldres, a.cout, a.rows_q, a.ldres))) {
+            launch_pdl(conv_tc_kernel<2>, dim3(grid), dim3(TC2_THREADS), smem, st, v, L, tm, tmr, tmx);
+            g_launch_count++;
+            check_launch("conv_tc_tma");
+            return true;
+        }
+        if (!plan(a, L, smem, false)) return false;          // no tensor map for these buffers: row-per-thread epilogue
+        v = a;
+        if (L.cat) v.wtc = a.wcat;
+        if (L.tma_in && !make_in_map(&tmx, a.x, a.rows_in, a.cin, a.ldx, L.win)) L.tma_in = 0;
     }
     launch_pdl(conv_tc_kernel<0>, dim3(grid), dim3(TC2_THREADS), smem, st, v, L, tm, tmr, tmx);
     g_launch_count++;

@@ -86,6 +86,12 @@ CASES = [
     # agent's "store has been read out" signal is the only thing that orders it (regression: WAR race)
     (148 * 128 * 6 + 77, 32, 32, 3, 1, 0.1, 0, False, 1.0, False, None),
     (148 * 128 * 4, 32, 32, 11, 5, 0.1, 0, False, 1.0, True, 148 * 128 * 4 - 1000),
+    # coalesced epilogue (conv_tc MODE 1: 64- / 96- / 128-channel outputs turned through shared memory): ragged row
+    # counts inside a warp's 32 rows, gap rows under accumulate, ReLU, negative scale, 3 column chunks
+    (1000, 64, 64, 11, 5, 0.1, 0, True, 1 / 3, True, 901),
+    (148 * 128 * 2 + 45, 128, 128, 7, 3, 0.1, 1, True, 1.0, False, 148 * 128 * 2),
+    (333, 192, 96, 1, 1, 1.0, 0, True, -1.0, True, 301),
+    (148 * 128 * 7 + 19, 64, 64, 3, 1, 0.1, 0, False, 1.0, False, None),
 ]
 
 # backend 2 = conv_tf.cu (tcgen05 3xTF32 with chunk-flushed accumulation; the text-encoder / duration-predictor
