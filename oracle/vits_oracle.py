@@ -1,4 +1,5 @@
-"""ORACLE — TEST INFRASTRUCTURE ONLY.  **Parity unpinned** (see below).
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  **Parity unpinned against the reference itself** (see below); checked against an
+independent third-party implementation of the same published algorithm instead (last paragraph).
 
 CPU restatement (PyTorch fp32, optional fp64 shadow) of the arithmetic the reference runs
 inside ``ort::Session::run`` at ``crates/sonata/models/piper/src/lib.rs:362-379``: the Piper
@@ -23,6 +24,14 @@ on what the reference does pin at its call sites:
 * streaming split: encoder outputs named ``z``, ``y_mask`` and a decoder on frame slices of
   axis 2 (``piper/src/lib.rs:681-735, 793-840``) -> ``encode`` / ``decode``;
 * hop = 256 samples per frame (``piper/src/lib.rs:910``).
+
+Second opinion (what this restatement IS checked against): Hugging Face ``transformers`` 5.5.0 ``VitsModel`` -- an
+independent implementation of the published VITS network, not derived from Piper and not written here -- loaded with
+the same synthetic high-quality (ResBlock1, en_US-ryan-high architecture) voice reproduces this oracle's waveform to
+2e-6 .. 4e-6, frame counts identical, on the deterministic AND the stochastic path (``tests/hf_reference.py``,
+``tests/test_hf_pin.py``, fixtures + generator under ``tests/golden/hf/``).  Not covered by it: the ResBlock2 wiring of
+the medium voices (transformers implements ResBlock1 only) and anything Piper's ONNX export may do differently from
+the published model code.
 
 Every function takes ``W``: dict name -> torch tensor with Piper state-dict names.
 """
