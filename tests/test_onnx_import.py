@@ -132,3 +132,24 @@ def test_multi_speaker_import_and_garbage(tmp_path):
     bad.write_bytes(_ld(2, b"not a model"))
     with pytest.raises(ValueError, match="GraphProto"):
         onnx_import.read_initializers(str(bad))
+
+
+REAL_ONNX = "/root/reference/deps/libtashkeel/crates/core/data/ort/model.onnx"
+
+
+@pytest.mark.skipif(not os.path.exists(REAL_ONNX), reason="the reference checkout (build container only) holds the file")
+def test_reader_parses_a_real_exported_onnx_file():
+    """Every other test here reads files written by this suite's own writer.  The one ONNX file a real exporter produced
+    that exists offline is the libtashkeel model vendored by the reference (a torch.onnx export, not a Piper voice): the
+    hand-rolled protobuf reader must get its initialisers out -- names, dims, dtypes, raw payloads -- and account for
+    nearly all of the file's bytes."""
+    t = onnx_import.read_initializers(REAL_ONNX)
+    assert len(t) == 127
+    assert t["char_emb.weight"].shape == (54, 56) and t["char_emb.weight"].dtype == np.float32
+    assert t["attn_layers.0.ccm.batchnorm.running_var"].shape == (112,)
+    assert all(np.isfinite(v).all() for v in t.values() if v.dtype.kind == "f")
+    assert all(v.size > 0 for v in t.values())
+    payload = sum(v.nbytes for v in t.values())
+    assert 0.95 * os.path.getsize(REAL_ONNX) < payload < os.path.getsize(REAL_ONNX)
+    # spot values: an embedding table of a trained model is O(1), LayerNorm gains sit around 1
+    assert 0.5 < float(np.abs(t["char_emb.weight"]).max()) < 10 and 0.2 < float(t["attn_layers.0.attn.layernorm.weight"].mean()) < 2
