@@ -22,10 +22,15 @@ import numpy as np
 import torch
 
 
-def build_hf_model(a: dict):
-    """`a`: an architecture dict of sonata_b200.voicegen.ARCH (resblock must be 1)."""
+def build_hf_model(a: dict, decoder: bool = True):
+    """`a`: an architecture dict of sonata_b200.voicegen.ARCH.  decoder=False builds a throw-away one-stage vocoder so that
+    voices whose HiFi-GAN transformers cannot express (ResBlock2: the medium voices) can still be compared on everything
+    in front of it through `VitsModelOutput.spectrogram` (= the flow output z)."""
     from transformers import VitsConfig, VitsModel
-    assert a["resblock"] == 1, "transformers' VITS implements ResBlock1 only"
+    if decoder:
+        assert a["resblock"] == 1, "transformers' VITS implements ResBlock1 only"
+    else:
+        a = dict(a, up_init=16, up_rates=(2,), up_kernels=(4,), res_kernels=(3,), res_dils=((1,),))
     cfg = VitsConfig(
         vocab_size=a["n_vocab"], hidden_size=a["hidden"], num_hidden_layers=a["layers"],
         num_attention_heads=a["heads"], window_size=a["window"], use_bias=True, ffn_dim=a["filter"],
@@ -60,7 +65,7 @@ def _set_weight_normed(conv, w):
     _set(par.original1, w)
 
 
-def load_piper_tensors(model, T: dict, a: dict):
+def load_piper_tensors(model, T: dict, a: dict, decoder: bool = True):
     """Copy a Piper-named tensor dict (sonata_b200.voicegen.make_tensors) into the HF model, name by name."""
     te = model.text_encoder
     _set(te.embed_tokens.weight, T["enc_p.emb.weight"])
@@ -112,6 +117,8 @@ def load_piper_tensors(model, T: dict, a: dict):
             _set(fl.wavenet.res_skip_layers[l].bias, T[p + f"enc.res_skip_layers.{l}.bias"])
         _set(fl.conv_post.weight, T[p + "post.weight"]); _set(fl.conv_post.bias, T[p + "post.bias"])
 
+    if not decoder:
+        return model
     dec = model.decoder
     _set(dec.conv_pre.weight, T["dec.conv_pre.weight"]); _set(dec.conv_pre.bias, T["dec.conv_pre.bias"])
     nk = len(a["res_kernels"])
@@ -139,6 +146,7 @@ def hf_infer(model, ids, noise_scale: float, length_scale: float, noise_w: float
     with torch.no_grad():
         out = model(input_ids=ids, attention_mask=torch.ones_like(ids))
     wav = out.waveform[0].float().numpy().copy()
+    hf_infer.last_spectrogram = out.spectrogram[0].float().numpy().copy()      # [inter, frames]: the flow output z
     frames = wav.shape[0] // int(np.prod(model.config.upsample_rates))
     torch.manual_seed(seed)
     eps_w = torch.randn(1, 2, ids.shape[1])

@@ -77,6 +77,26 @@ def test_oracle_against_live_transformers_run(hf_model, oracle_weights):
         assert float(np.abs(got - wav).max()) < TOL_ORACLE, scales
 
 
+def test_medium_voice_up_to_the_vocoder_against_live_transformers_run(oracle_weights):
+    """transformers has no ResBlock2, so the medium voice cannot be run end to end there; everything in FRONT of the
+    vocoder can: text encoder, duration predictor, alignment and flow of the medium voice (its own weights and gains)
+    against `VitsModelOutput.spectrogram`."""
+    pytest.importorskip("transformers")
+    import hf_reference as hf
+    a = voicegen.ARCH["medium"]
+    m = hf.load_piper_tensors(hf.build_hf_model(a, decoder=False), voicegen.make_tensors("medium"), a, decoder=False)
+    W = oracle_weights("medium")
+    ids = vo.synthetic_ids(40, utt=3)
+    for scales, seed in (((0.0, 1.0, 0.0), 0), ((0.667, 1.1, 0.8), 9)):
+        _, ew, ez = hf.hf_infer(m, ids, *scales, seed=seed)
+        z_hf = hf.hf_infer.last_spectrogram
+        st = {}
+        vo.encode(W, ids, list(scales), eps_w=ew[None] if scales[2] else None, eps_z=ez[None] if scales[0] else None, stages=st)
+        z = st["z"][0].numpy()
+        assert z.shape == z_hf.shape, (scales, z.shape, z_hf.shape)           # identical frame count
+        assert float(np.abs(z - z_hf).max()) < 5e-5, scales                    # z is O(1..5)
+
+
 # ------------------------------------------------------------------------------------------------ CUDA path
 def _run_cuda(m, ids, scales, eps_w, eps_z):
     from sonata_b200.job import SynthesisJob
