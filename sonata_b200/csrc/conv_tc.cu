@@ -46,6 +46,12 @@
 
 namespace sb200 {
 
+static int tc_num_sms() {
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+    return n;
+}
+
 namespace {
 
 using namespace tcx;
@@ -70,6 +76,8 @@ struct TcLaunch {
     int depth;       // window loads in flight per pipeline (< na: see plan())
     int v8;          // every epilogue operand is 32-byte aligned: 256-bit global accesses
     int tma_st;      // MODE 2: output tile leaves through a TMA tensor store
+    int pairs;       // streamed weights: the CTA walks PAIRS of m-tiles that share the n-tile (pipeline p takes member p), and the
+                     // two pipelines consume ONE weight ring -- every stage is fetched from L2 once per 256 output rows
     int nstg;        // MODE 2: staging tiles per pipeline (1 = residual-in / output, 2 = + previous value of an accumulated buffer)
     // "cat" mode (nt <= 64, resident weights): the weight image of a tap stacks the hi rows and the lo rows along N,
     // so  A_hi x [W_hi ; W_lo]  is ONE MMA of N = 2*nt (columns [0,nt) = hi*hi, [nt,2nt) = hi*lo) and  A_lo x W_hi
@@ -130,8 +138,20 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
     const int per_tile = nkb * a.ntaps;
     const int npairs = (a.ntaps + 1) >> 1;
     const int wper = L.cat ? nkb * npairs : per_tile;            // weight images per tile
-    const int total_tiles = L.ntiles_m * L.ntiles_n;
-    const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // tile tl of this CTA -> (m-tile, n-tile).  Plain: tiles blockIdx.x, +gridDim.x, ... over (m, n).  Pairs: the same walk
+    // over (m-pair, n); tile 2k + p is member p of the CTA's k-th pair (an odd m-tile count leaves one empty member whose
+    // rows lie past the end of the array: loads are zero-filled, nothing is stored).
+    const int total_tiles = L.pairs ? ((L.ntiles_m + 1) / 2) * L.ntiles_n : L.ntiles_m * L.ntiles_n;
+    const int my_units = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int my_tiles = L.pairs ? 2 * my_units : my_units;
+    auto tile_m = [&](int tl) {
+        if (L.pairs) return 2 * (((int)blockIdx.x + (tl >> 1) * (int)gridDim.x) / L.ntiles_n) + (tl & 1);
+        return ((int)blockIdx.x + tl * (int)gridDim.x) / L.ntiles_n;
+    };
+    auto tile_n = [&](int tl) {
+        if (L.pairs) return ((int)blockIdx.x + (tl >> 1) * (int)gridDim.x) % L.ntiles_n;
+        return ((int)blockIdx.x + tl * (int)gridDim.x) % L.ntiles_n;
+    };
 
     if (warp == 3) {
         // all barriers are initialised by one warp in parallel (a single thread doing the ~120 inits one after the other
@@ -140,7 +160,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
         constexpr int NB = 2 * TC_MAX_WRING + 6 * TC_MAX_ASTAGES + 12;
         for (int i = lane; i < NB; i += 32) {
             const int j = i - 2 * TC_MAX_WRING;
-            const uint32_t cnt = j < 0 ? 1u : j < 8 ? (uint32_t)TC_GROUP : j < 20 ? 1u : j < 24 ? 128u : j < 32 ? 1u : j < 34 ? 128u : 1u;
+            const uint32_t cnt = j < 0 ? ((L.pairs && i >= TC_MAX_WRING) ? 2u : 1u) : j < 8 ? (uint32_t)TC_GROUP : j < 20 ? 1u : j < 24 ? 128u : j < 32 ? 1u : j < 34 ? 128u : 1u;
             mbar_init(smem_u32(&bars[i]), cnt);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -170,7 +190,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
     // are busy streaming)
     const int nch = L.nt / 32;                       // MODE 2: 32-column chunks per tile, one staged item each
     // MODE 2 item `it` of pipeline pp: tile pp + 2 * (it / nch), chunk it % nch
-    auto item_row = [&](int pp, int it) { return ((int)blockIdx.x + (pp + 2 * (it / nch)) * (int)gridDim.x) / L.ntiles_n * 128; };
+    auto item_row = [&](int pp, int it) { return tile_m(pp + 2 * (it / nch)) * 128; };
     auto agent_fetch = [&](int pp, int it) {
         const uint32_t st = smem_u32(EX + (size_t)pp * L.nstg * TC_OUT_BYTES);     // [0] residual-in / output, [1] previous
         const uint32_t bytes = (a.res ? TC_OUT_BYTES : 0) + (a.acc0 ? TC_OUT_BYTES : 0);
@@ -199,9 +219,11 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
         const int p = warp;
         const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
         uint8_t* Ap = A0 + (size_t)p * L.na * a_buf;
-        uint8_t* Wp = L.resident ? W0 : W0 + (size_t)p * L.ws * w_stage;
-        uint64_t* wf = L.resident ? w_full : w_full + p * L.ws;
-        uint64_t* we = L.resident ? w_empty : w_empty + p * L.ws;
+        const bool own_ring = !L.resident && !L.pairs;           // pairs: one ring of 2 * ws slots for both pipelines
+        uint8_t* Wp = own_ring ? W0 + (size_t)p * L.ws * w_stage : W0;
+        uint64_t* wf = own_ring ? w_full + p * L.ws : w_full;
+        uint64_t* we = own_ring ? w_empty + p * L.ws : w_empty;
+        const int wr = L.pairs ? 2 * L.ws : L.ws;                 // ring slots seen by this pipeline
         int lit = 0, lwit = 0;                 // pipeline-local stage / weight-stage counters
         for (int tl = p, lt = 0; tl < my_tiles; tl += 2, lt++) {
             const int accs = lt & 1;           // accumulator stage within the pipeline
@@ -221,8 +243,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                         ws = L.cat ? kb * npairs + (t >> 1) : kb * a.ntaps + t;
                         if (lt == 0) { mbar_wait(smem_u32(&wf[ws]), 0); tc_fence_after(); }   // loaded once, stays
                     } else {
-                        ws = lwit % L.ws;
-                        mbar_wait(smem_u32(&wf[ws]), (uint32_t)((lwit / L.ws) & 1));
+                        ws = lwit % wr;
+                        mbar_wait(smem_u32(&wf[ws]), (uint32_t)((lwit / wr) & 1));
                         tc_fence_after();
                     }
                     const uint32_t wimg = (smem_u32(Wp + (size_t)ws * w_stage) >> 4) + (L.cat ? (uint32_t)(t & 1) * 4u : 0u);
@@ -273,15 +295,27 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                         bulk_g2s(smem_u32(W0 + (size_t)s * w_stage), wsrc + (size_t)s * w_stage, w_stage, smem_u32(&w_full[s]));
                     }
                 }
+            } else if (L.pairs) {
+                if (p == 0) {                                   // one stream feeds both pipelines (w_empty counts two commits)
+                    const int wr = 2 * L.ws;
+                    int lwit = 0;
+                    for (int tl = 0; tl < my_tiles; tl += 2) {
+                        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wtc) + (size_t)tile_n(tl) * per_tile * w_stage;
+                        for (int i = 0; i < per_tile; i++, lwit++) {
+                            const int ws = lwit % wr;
+                            mbar_wait(smem_u32(&w_empty[ws]), (uint32_t)(((lwit / wr) & 1) ^ 1));
+                            mbar_expect_tx(smem_u32(&w_full[ws]), w_stage);
+                            bulk_g2s(smem_u32(W0 + (size_t)ws * w_stage), wsrc + (size_t)i * w_stage, w_stage, smem_u32(&w_full[ws]));
+                        }
+                    }
+                }
             } else {
                 uint8_t* Wp = W0 + (size_t)p * L.ws * w_stage;
                 uint64_t* wf = w_full + p * L.ws;
                 uint64_t* we = w_empty + p * L.ws;
                 int lwit = 0;
                 for (int tl = p; tl < my_tiles; tl += 2) {
-                    const int tg = (int)blockIdx.x + tl * (int)gridDim.x;
-                    const int n_tile = tg % L.ntiles_n;
-                    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wtc) + (size_t)n_tile * per_tile * w_stage;
+                    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wtc) + (size_t)tile_n(tl) * per_tile * w_stage;
                     for (int i = 0; i < per_tile; i++, lwit++) {
                         const int ws = lwit % L.ws;
                         mbar_wait(smem_u32(&we[ws]), (uint32_t)(((lwit / L.ws) & 1) ^ 1));
@@ -325,8 +359,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
         const int depth = L.depth;                     // stages in flight
         auto issue_stage = [&](int j) {
             const int lt = j / nkb, kb = j - lt * nkb;
-            const int tg = (int)blockIdx.x + (p + 2 * lt) * (int)gridDim.x;
-            const int rbase = (tg / L.ntiles_n) * 128 + a.min_off;
+            const int rbase = tile_m(p + 2 * lt) * 128 + a.min_off;
             const int as = j % L.na;
             mbar_wait(smem_u32(&a_empty[p * TC_MAX_ASTAGES + as]), (uint32_t)(((j / L.na) & 1) ^ 1));
             if (p == 0 && gt == 0 && kb == 0) TC_TRACE(a, lt, 0);
@@ -371,8 +404,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
             else asm volatile("cp.async.wait_group 0;" ::: "memory");
             {
                 const int lt_ = j / nkb;
-                const int tg_ = (int)blockIdx.x + (p + 2 * lt_) * (int)gridDim.x;
-                const int rb_ = (tg_ / L.ntiles_n) * 128 + a.min_off;
+                const int rb_ = tile_m(p + 2 * lt_) * 128 + a.min_off;
                 if (L.tma_in || (L.bulk_in && rb_ >= 0 && rb_ + L.win <= a.rows_in)) {
                     const int as_ = j % L.na;
                     mbar_wait(smem_u32(&raw_full[p * TC_MAX_ASTAGES + as_]), (rawpar >> as_) & 1u);
@@ -448,8 +480,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
             const int nitems = ((my_tiles - p + 1) / 2) * nch;
             if (self && row == 0 && nitems) agent_fetch(p, 0);
             for (int tl = p, lt = 0; tl < my_tiles; tl += 2, lt++) {
-                const int tg = (int)blockIdx.x + tl * (int)gridDim.x;
-                const int q = (tg / L.ntiles_n) * 128 + row;
+                const int q = tile_m(tl) * 128 + row;
                 const int acc = p + 2 * (lt & 1);
                 const bool valid = q < a.rows_q && row_valid(a.map, q);
                 mbar_wait(smem_u32(&acc_full[acc]), (uint32_t)((lt >> 1) & 1));
@@ -511,9 +542,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
         } else {
         const bool gate = a.act == ACT_GATE;
         for (int tl = p, lt = 0; tl < my_tiles; tl += 2, lt++) {
-            const int tg = (int)blockIdx.x + tl * (int)gridDim.x;
-            const int q = (tg / L.ntiles_n) * 128 + row;
-            const int n0 = (tg % L.ntiles_n) * L.nt;
+            const int q = tile_m(tl) * 128 + row;
+            const int n0 = tile_n(tl) * L.nt;
             const int acc = p + 2 * (lt & 1);
             const bool inrange = q < a.rows_q;
             const bool valid = inrange && row_valid(a.map, q);
@@ -682,6 +712,9 @@ bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem, bool allow_tma_st = true
                 !SB_ENV_ONCE("SB200_TC_NOTMAIN")) ? 1 : 0;
     L.resident = (L.ntiles_n == 1 && per_tile <= TC_MAX_WRING && per_tile * w_stage + 4 * a_buf + bar_bytes <= budget) ? 1 : 0;
     if (L.tma_st && !L.resident && SB_ENV_ONCE("SB200_TC_TMAST_RESONLY")) return plan(a, L, smem, false);
+    // (small launches keep one tile per CTA: with fewer tiles than 2 x SMs, pairing halves the CTAs and couples two tiles to
+    //  one weight stream for nothing -- C1 flow 0.90 -> 1.00 ms)
+    L.pairs = (!L.resident && L.ntiles_m * L.ntiles_n >= 2 * tc_num_sms() && !SB_ENV_ONCE("SB200_TC_NOPAIRS")) ? 1 : 0;
     const int wper_cat = (a.cin / 32) * ((a.ntaps + 1) / 2);
     if (a.wcat && L.tma_st && L.nt <= 64 && L.resident && wper_cat * 2 * w_stage + 4 * a_buf + bar_bytes <= budget && !SB_ENV_ONCE("SB200_TC_NOCAT")) {
         L.cat = 1; L.accw = 2 * L.nt;
@@ -753,12 +786,6 @@ bool conv_tc_supported(const ConvArgs& a) {
     return plan(a, L, smem);
 }
 
-static int tc_num_sms() {
-    static int n = 0;
-    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
-    return n;
-}
-
 void launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     if (!try_launch_conv_tc(a, st)) launch_conv_simt(a, st);
 }
@@ -778,8 +805,11 @@ bool try_launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     memset(&tmr, 0, sizeof(tmr));
     memset(&tmx, 0, sizeof(tmx));
     if (!plan(a, L, smem)) return false;
-    const int tiles = L.ntiles_m * L.ntiles_n;
-    const int grid = tiles < tc_num_sms() ? tiles : tc_num_sms();
+    auto grid_of = [&]() {
+        const int units = L.pairs ? ((L.ntiles_m + 1) / 2) * L.ntiles_n : L.ntiles_m * L.ntiles_n;
+        return units < tc_num_sms() ? units : tc_num_sms();
+    };
+    int grid = grid_of();
     v = a;
     if (L.cat) v.wtc = a.wcat;
     if (L.tma_in && !make_in_map(&tmx, a.x, a.rows_in, a.cin, a.ldx, L.win)) L.tma_in = 0;
@@ -792,6 +822,7 @@ bool try_launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
             return true;
         }
         if (!plan(a, L, smem, false)) return false;          // no tensor map for these buffers: row-per-thread epilogue
+        grid = grid_of();
         v = a;
         if (L.cat) v.wtc = a.wcat;
         if (L.tma_in && !make_in_map(&tmx, a.x, a.rows_in, a.cin, a.ldx, L.win)) L.tma_in = 0;
