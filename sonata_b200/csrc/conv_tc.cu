@@ -23,16 +23,20 @@
 //     address is shifted by off_t rows (the swizzle is a function of the absolute smem address), so a k-tap
 //     conv stages its input once and issues k x 6 (cat mode: k x 4) MMAs on it;
 //   * weights: pre-split, pre-swizzled tile images written at voice-load time; one cp.async.bulk (UBLKCP)
-//     per (K-block, tap) stage, resident in smem for the whole CTA when they fit;
+//     per (K-block, tap) stage, resident in smem for the whole CTA when they fit; otherwise streamed through a
+//     ring -- on large launches ONE ring for both half-pipelines, which then walk the two m-tiles of a pair
+//     that shares the n-tile, so a stage is fetched from L2 once per 256 output rows;
 //   * MMA: tcgen05.mma.kind::f16 (UTCHMMA), issued from warp-uniform code under elect.sync;
 //     tcgen05.commit releases ring slots / publishes the accumulator;
 //   * epilogue, MODE 0 (general): tcgen05.ld 32x32b.x32 (LDTM) -> bias / gate / residual / scale /
 //     accumulate -> HBM with 256-bit row-per-thread accesses, the residual / read-modify-write operands
 //     prefetched before the accumulator is awaited;
-//   * epilogue, MODE 2 (32-channel outputs): residual and read-modify-write tiles arrive by TMA tensor
-//     loads into SWIZZLE_128B staging tiles, the result is written over the residual tile in place and
-//     leaves with one TMA tensor store per tile, all issued by an agent lane of the idle weight warp -- the
-//     SM's load/store path sees no global traffic at all (ncu: that path, not HBM, bounded these layers);
+//   * epilogue, MODE 2 (32- and 64-channel outputs in one column tile): the residual and read-modify-write
+//     operands of a 32-column chunk arrive by TMA tensor loads into SWIZZLE_128B staging tiles, the result is
+//     written over the residual tile in place and leaves with one TMA tensor store per chunk, issued by an
+//     agent lane of the idle weight warp (resident weights) or by thread 0 of the epilogue group itself
+//     (streamed weights) -- the SM's load/store path sees no global traffic at all (that path, not HBM,
+//     bounded these layers: its row-per-thread accesses also slow the producers' conversion 2x);
 // Persistent CTAs (one per SM) walk tiles blockIdx.x, +gridDim.x, ...; mbarrier pipelines (activation
 // ring, weight ring, 4-stage TMEM accumulator ring, MODE 2 staging) run across tile boundaries.
 // Warps: w0/w1 MMA issuers on alternating tiles (w0 also allocates TMEM), w2/w3 weight producers and
