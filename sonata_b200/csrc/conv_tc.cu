@@ -67,6 +67,8 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
 
 struct TcLaunch {
     int nt;          // columns per CTA tile (multiple of 32, <= 128)
+    int wnt;         // rows of a weight IMAGE (the voice's tile width); nt == wnt, or wnt / 2 on small launches: the CTA
+                     // then takes half an image (a 64-row half keeps the image's swizzle: 64 % 8 == 0)
     int win;         // window rows (multiple of 8)
     int na;          // activation ring stages PER PIPELINE
     int ws;          // weight stages: all (K-block, tap) stages when resident (shared), else ring stages PER PIPELINE
@@ -294,6 +296,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
     } else if (warp < 4) {
         // ===================== weight producer of pipeline p = warp - 2 =====================
         const int p = warp - 2;
+        // a stage is one image, or the `nt`-row part of an image that is `wnt` rows tall (see TcLaunch::wnt)
+        const size_t w_image = (size_t)L.wnt * 128u;
+        auto w_image0 = [&](int n_tile) {
+            const int vf = L.wnt / L.nt;
+            return reinterpret_cast<const uint8_t*>(a.wtc) + (size_t)(n_tile / vf) * per_tile * w_image + (size_t)(n_tile % vf) * w_stage;
+        };
         {
         if (lane == 0) {
             if (L.resident) {
@@ -309,12 +317,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                     const int wr = 2 * L.ws;
                     int lwit = 0;
                     for (int tl = 0; tl < my_tiles; tl += 2) {
-                        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wtc) + (size_t)tile_n(tl) * per_tile * w_stage;
+                        const uint8_t* wsrc = w_image0(tile_n(tl));
                         for (int i = 0; i < per_tile; i++, lwit++) {
                             const int ws = lwit % wr;
                             mbar_wait(smem_u32(&w_empty[ws]), (uint32_t)(((lwit / wr) & 1) ^ 1));
                             mbar_expect_tx(smem_u32(&w_full[ws]), w_stage);
-                            bulk_g2s(smem_u32(W0 + (size_t)ws * w_stage), wsrc + (size_t)i * w_stage, w_stage, smem_u32(&w_full[ws]));
+                            bulk_g2s(smem_u32(W0 + (size_t)ws * w_stage), wsrc + (size_t)i * w_image, w_stage, smem_u32(&w_full[ws]));
                         }
                     }
                 }
@@ -324,12 +332,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                 uint64_t* we = w_empty + p * L.ws;
                 int lwit = 0;
                 for (int tl = p; tl < my_tiles; tl += 2) {
-                    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wtc) + (size_t)tile_n(tl) * per_tile * w_stage;
+                    const uint8_t* wsrc = w_image0(tile_n(tl));
                     for (int i = 0; i < per_tile; i++, lwit++) {
                         const int ws = lwit % L.ws;
                         mbar_wait(smem_u32(&we[ws]), (uint32_t)(((lwit / L.ws) & 1) ^ 1));
                         mbar_expect_tx(smem_u32(&wf[ws]), w_stage);
-                        bulk_g2s(smem_u32(Wp + (size_t)ws * w_stage), wsrc + (size_t)i * w_stage, w_stage, smem_u32(&wf[ws]));
+                        bulk_g2s(smem_u32(Wp + (size_t)ws * w_stage), wsrc + (size_t)i * w_image, w_stage, smem_u32(&wf[ws]));
                     }
                 }
             }
@@ -698,7 +706,7 @@ bool epi_v8_ok(const ConvArgs& a) {
 
 bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem, bool allow_tma_st = true) {
     if (!a.wtc || a.tc_nt <= 0 || a.tc_nt > 128) return false;
-    L.nt = a.tc_nt;
+    L.nt = L.wnt = a.tc_nt;
     L.v8 = epi_v8_ok(a) ? 1 : 0;
     // TMA-staged epilogue: one output buffer, plain row mapping, whole 32-column chunks (32 / 64 / 128 output channels in
     // ONE column tile).  SB200_TC_TMAST_MAXC caps the channel count (A/B against the row-per-thread epilogue).
@@ -709,6 +717,16 @@ bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem, bool allow_tma_st = true
                 !SB_ENV_ONCE("SB200_TC_NOTMAST")) ? 1 : 0;
     if (a.res && (a.ldres & 3)) L.tma_st = 0;
     L.nstg = a.acc0 ? 2 : 1;
+    // Small launches (a single utterance): a 128-column tile costs 160 cycles per MMA from its one issuing warp and a
+    // 128-column epilogue, ~25 us for a k5 layer, while most SMs idle: take the narrowest part of an image (a multiple of
+    // 32 rows that divides it) that still leaves no more tiles than SMs.  Not for the layers of the TMA-staged epilogue:
+    // their arithmetic (cat mode, epilogue rounding) differs from MODE 0, and an utterance must come out bit-identical
+    // whether it is synthesised alone or in a batch (tested); tile WIDTH alone changes no summation order.
+    if (!L.tma_st && a.cout % a.tc_nt == 0 && !SB_ENV_ONCE("SB200_TC_NOHALF")) {
+        const int mt = (a.rows_q + 127) / 128;
+        for (int nt = 32; nt < a.tc_nt; nt += 32)
+            if (a.tc_nt % nt == 0 && mt * (a.cout / nt) <= tc_num_sms()) { L.nt = nt; break; }
+    }
     L.win = (128 + a.span + 7) & ~7;
     if (L.win * 4 > TC_MAXCH * TC_GROUP) return false;
     L.cat = 0; L.accw = L.nt; L.idesc2 = 0;

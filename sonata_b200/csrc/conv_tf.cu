@@ -52,6 +52,8 @@ constexpr int TF_NTH_MAX = 96;
 
 struct TfLaunch {
     int nth;         // columns of a tile (per issuer and per weight stage): 96 / 64 / 32
+    int wnth;        // rows of a weight IMAGE (tf_nth_for); nth == wnth, or 32 on small launches: the CTA then takes a 32-row
+                     // part of the hi image and of the lo image (two copies per stage; 32 % 8 == 0 keeps the swizzle)
     int win;         // window rows (multiple of 8)
     int na, nw;      // activation ring stages per issuer, weight ring stages
     int ntiles_mp;   // pairs of 128-row m-tiles
@@ -213,15 +215,23 @@ __global__ void __launch_bounds__(TfCfg<GM>::THREADS, 1) conv_tf_kernel(const Co
             const int per_tile = nkb_conv * a.ntaps;
             const uint32_t w_stage = 2 * w_img;
             int lw = 0;
+            const int vf = L.wnth / L.nth;                       // tile = 1 / vf of an image
+            const size_t src_img = (size_t)L.wnth * 128u;        // one image in the voice (a stage = hi image + lo image)
             for (int tl = 0; tl < my_tiles; tl++) {
                 const int tg = (int)blockIdx.x + tl * (int)gridDim.x;
                 const int n_tile = tg % L.ntiles_n;
-                const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wtf) + (size_t)n_tile * per_tile * w_stage;
+                const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wtf) + (size_t)(n_tile / vf) * per_tile * 2 * src_img +
+                                      (size_t)(n_tile % vf) * w_img;
                 for (int i = 0; i < per_tile; i++, lw++) {
                     const int ws = lw % L.nw;
                     mbar_wait(smem_u32(&w_empty[ws]), (uint32_t)(((lw / L.nw) & 1) ^ 1));
                     mbar_expect_tx(smem_u32(&w_full[ws]), w_stage);
-                    bulk_g2s(smem_u32(W0 + (size_t)ws * w_stage), wsrc + (size_t)i * w_stage, w_stage, smem_u32(&w_full[ws]));
+                    const uint8_t* st = wsrc + (size_t)i * 2 * src_img;
+                    if (vf == 1) bulk_g2s(smem_u32(W0 + (size_t)ws * w_stage), st, w_stage, smem_u32(&w_full[ws]));
+                    else {
+                        bulk_g2s(smem_u32(W0 + (size_t)ws * w_stage), st, w_img, smem_u32(&w_full[ws]));
+                        bulk_g2s(smem_u32(W0 + (size_t)ws * w_stage + w_img), st + src_img, w_img, smem_u32(&w_full[ws]));
+                    }
                 }
             }
         }
@@ -414,6 +424,8 @@ __global__ void __launch_bounds__(TfCfg<GM>::THREADS, 1) conv_tf_kernel(const Co
 // load + conversion latency (ncu: tensor pipe ~50 %).  1x1 layers: an activation stage feeds only 12 MMAs (~1000 cycles)
 // while a TMA load + conversion takes ~2000, so they want THREE stages per issuer, which only fits next to 64-column
 // weight stages (ncu with 96 columns / 2 stages: tensor pipe 12-20 %, 35-57 TFLOP/s against 150-160 for the k3 layers).
+int tf_num_sms();
+
 int tf_nth_for(int cout, int ntaps) {
     if (ntaps == 1 && cout % 64 == 0) return 64;
     if (cout % 96 == 0) return 96;
@@ -430,11 +442,14 @@ bool plan(const ConvArgs& a, TfLaunch& L, size_t& smem) {
     auto al32 = [](const void* p, int ld) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 31) == 0 && (ld & 7) == 0); };
     if (!al32(a.y0, a.ldy0) || !al32(a.res, a.ldres)) return false;
     if ((a.ldx & 3) || (reinterpret_cast<uintptr_t>(a.x) & 15)) return false;
-    L.nth = tf_nth_for(a.cout, a.ntaps);
+    L.nth = L.wnth = tf_nth_for(a.cout, a.ntaps);
     if (!L.nth) return false;
     L.win = (128 + a.span + 7) & ~7;
     if (L.win > 256) return false;
     L.ntiles_mp = (a.rows_q + 255) / 256;
+    // Small launches (a single utterance): 32-column tiles on more SMs -- the K loop of a tile costs the same number of
+    // MMAs whatever its width, but each is cheaper and the flush / epilogue of a tile shrinks with its width.
+    if (L.wnth > 32 && L.ntiles_mp * (a.cout / 32) <= tf_num_sms() && !SB_ENV_ONCE("SB200_TF_NONARROW")) L.nth = 32;
     L.ntiles_n = a.cout / L.nth;
     L.chunk_kb = a.ntaps == 1 ? 2 : 1;
     { const char* e = SB_ENV_ONCE("SB200_TF_CHUNK"); if (e && atoi(e) >= 1) L.chunk_kb = atoi(e); }     // accuracy experiments
@@ -524,7 +539,7 @@ void launch_gemm_tf(const TfGemm& g, cudaStream_t st) {
     a.in_slope = 1.f; a.ntaps = 1; a.cin = 32; a.cout = g.nth;
     a.y0 = g.y; a.ldy0 = g.ldy; a.res = g.res; a.ldres = g.ldy; a.scale = g.scale; a.split = g.nth; a.orow_mul = 1;
     TfLaunch L{};
-    L.nth = g.nth; L.win = 128; L.ntiles_mp = g.ntiles; L.ntiles_n = 1; L.chunk_kb = 2;
+    L.nth = L.wnth = g.nth; L.win = 128; L.ntiles_mp = g.ntiles; L.ntiles_n = 1; L.chunk_kb = 2;
     L.tmem_cols = 32;
     while (L.tmem_cols < 4 * L.nth) L.tmem_cols <<= 1;
     L.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(L.nth >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
