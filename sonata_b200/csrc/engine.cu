@@ -123,9 +123,24 @@ Job* create_job(Voice* v, const long long* ids, const size_t* offs, size_t B, co
         // [heads*RX][Tp], B = V^T [H][RX] (the q/k/v projection stores V transposed).
         const int H = v->a.hidden, heads = v->a.heads, D = H / heads;
         j->att_tp = round_up(std::max(j->max_tx, 1), 64);      // key tile of the Q.K^T GEMM (64: see conv_tf.cu tf_nth_for)
+        // Small jobs (a single utterance): narrower column tiles put the same MMAs on more SMs (conv_tf.cu plan()); tile
+        // width changes no summation order, so results do not depend on it.
+        {
+            int sms = 148, dev = 0;
+            if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            long long wide_s = 0, wide_o = 0;
+            for (size_t b = 0; b < B; b++) {
+                const int T = j->xsegs[b].len;
+                wide_s += (long long)heads * ((T + 255) / 256) * ((T + 63) / 64);
+                wide_o += (long long)heads * ((T + 255) / 256);
+            }
+            j->att_nth_s = wide_s * 2 <= sms ? 32 : 64;
+            j->att_nth_o = (D % 32 == 0 && wide_o * (D / 32) <= sms) ? 32 : D;
+        }
+        const int ks = j->att_nth_s, ko = j->att_nth_o;
         for (size_t b = 0; b < B; b++) {
             const int off = j->xsegs[b].off, T = j->xsegs[b].len;
-            const int nmp = (T + 255) / 256, nnt = (T + 63) / 64;
+            const int nmp = (T + 255) / 256, nnt = (T + ks - 1) / ks;
             for (int h = 0; h < heads; h++)
                 for (int mp = 0; mp < nmp; mp++) {
                     TfTile t{};
@@ -133,24 +148,26 @@ Job* create_job(Voice* v, const long long* ids, const size_t* offs, size_t B, co
                         const int r0 = (mp * 2 + m) * 128;
                         t.rows_valid[m] = std::max(0, std::min(128, T - r0));
                     }
-                    // Q.K^T: one tile per 64-key block
+                    // Q.K^T: one tile per block of ks keys
                     for (int nt = 0; nt < nnt; nt++) {
                         TfTile s = t;
                         for (int m = 0; m < 2; m++) {
                             s.a_row0[m] = off + (mp * 2 + m) * 128;
-                            s.out_off[m] = ((long long)h * j->RX + s.a_row0[m]) * j->att_tp + (long long)nt * 64;
+                            s.out_off[m] = ((long long)h * j->RX + s.a_row0[m]) * j->att_tp + (long long)nt * ks;
                         }
-                        s.a_col0 = h * D; s.b_row0 = off + nt * 64; s.b_col0 = H + h * D; s.nkb = D / 32;
+                        s.a_col0 = h * D; s.b_row0 = off + nt * ks; s.b_col0 = H + h * D; s.nkb = D / 32;
                         j->tiles_s.push_back(s);
                     }
                     // P.V: K runs over the utterance's keys in blocks of 32 (the softmax zero-fills up to the block end)
-                    TfTile o = t;
-                    for (int m = 0; m < 2; m++) {
-                        o.a_row0[m] = h * j->RX + off + (mp * 2 + m) * 128;
-                        o.out_off[m] = (long long)(off + (mp * 2 + m) * 128) * H + (long long)h * D;
+                    for (int c0 = 0; c0 < D; c0 += ko) {               // one tile per ko head-dim columns
+                        TfTile o = t;
+                        for (int m = 0; m < 2; m++) {
+                            o.a_row0[m] = h * j->RX + off + (mp * 2 + m) * 128;
+                            o.out_off[m] = (long long)(off + (mp * 2 + m) * 128) * H + (long long)h * D + c0;
+                        }
+                        o.a_col0 = 0; o.b_row0 = h * D + c0; o.b_col0 = off; o.nkb = (T + 31) / 32;
+                        j->tiles_o.push_back(o);
                     }
-                    o.a_col0 = 0; o.b_row0 = h * D; o.b_col0 = off; o.nkb = (T + 31) / 32;
-                    j->tiles_o.push_back(o);
                 }
         }
     }
@@ -471,11 +488,11 @@ void Job::run(float* d_out, size_t d_out_cap) {
         att_orel = C.dev.get<float>((size_t)RX * H);
         gs.a = qkv; gs.a_rows = RX; gs.a_cols = 3 * H; gs.lda = 3 * H;
         gs.b = qkv; gs.b_rows = RX; gs.b_cols = 3 * H; gs.ldb = 3 * H;
-        gs.nth = 64; gs.y = att_s; gs.ldy = att_tp; gs.res = nullptr; gs.scale = 1.0f / sqrtf((float)(H / a.heads));
+        gs.nth = att_nth_s; gs.y = att_s; gs.ldy = att_tp; gs.res = nullptr; gs.scale = 1.0f / sqrtf((float)(H / a.heads));
         gs.tiles = d_tiles_s; gs.ntiles = (int)tiles_s.size();
         go.a = att_s; go.a_rows = a.heads * RX; go.a_cols = att_tp; go.lda = att_tp;
         go.b = att_vt; go.b_rows = H; go.b_cols = RX; go.ldb = RX;
-        go.nth = 96; go.y = att; go.ldy = H; go.res = att_orel; go.scale = 1.f;
+        go.nth = att_nth_o; go.y = att; go.ldy = H; go.res = att_orel; go.scale = 1.f;
         go.tiles = d_tiles_o; go.ntiles = (int)tiles_o.size();
         tc_att_ok = gemm_tf_supported(gs) && gemm_tf_supported(go);
     }

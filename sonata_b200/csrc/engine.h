@@ -176,6 +176,7 @@ struct Job {
     // tensor-core attention (conv_tf.cu grouped GEMMs): tile tables built with the X layout, same for every layer
     std::vector<TfTile> tiles_s, tiles_o;      // Q.K^T tiles, P.V tiles
     int att_tp = 0;                            // key columns of a score row (multiple of 96)
+    int att_nth_s = 64, att_nth_o = 96;   // column tiles of the two attention GEMMs (narrower when the job is small)
     int* d_xseg_of_gran = nullptr; TfTile *d_tiles_s = nullptr, *d_tiles_o = nullptr;
     float *d_epsw = nullptr, *d_epsz = nullptr;
     float* d_wav = nullptr; bool wav_external = false;
