@@ -92,6 +92,10 @@ CASES = [
     (148 * 128 * 2 + 45, 128, 128, 7, 3, 0.1, 1, True, 1.0, False, 148 * 128 * 2),
     (333, 192, 96, 1, 1, 1.0, 0, True, -1.0, True, 301),
     (148 * 128 * 7 + 19, 64, 64, 3, 1, 0.1, 0, False, 1.0, False, None),
+    # streamed weights + TMA-staged epilogue + tile pairs with an ODD number of m-tiles: the last pair's second member lies
+    # wholly past the end of the array (loads zero-filled, its stores clipped by the tensor map)
+    (128 * 301 - 50, 64, 64, 11, 1, 0.1, 0, True, 1 / 3, True, 128 * 301 - 90),
+    (128 * 299, 128, 128, 7, 1, 0.1, 0, True, 1.0, False, None),
 ]
 
 # backend 2 = conv_tf.cu (tcgen05 3xTF32 with chunk-flushed accumulation; the text-encoder / duration-predictor
