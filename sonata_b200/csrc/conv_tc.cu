@@ -247,15 +247,20 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                 if (p == 0 && lane == 0 && kb == 0) TC_TRACE(a, lt, 3);
                 if (p == 0 && lane == 0 && lit < 7) TC_TRACE(a, 40 + lit, 4);
                 const uint32_t aimg = smem_u32(Ap + (size_t)as * a_buf) >> 4;
-                for (int t = 0; t < a.ntaps; t++, lwit++) {
+                for (int t = 0; t < a.ntaps; t++) {
                     int ws;
+                    // a streamed cat image holds a PAIR of taps: it is awaited at the even tap and released after the odd
+                    // (or last) one
+                    const bool pair_done = !L.cat || (t & 1) || t == a.ntaps - 1;
                     if (L.resident) {
                         ws = L.cat ? kb * npairs + (t >> 1) : kb * a.ntaps + t;
                         if (lt == 0) { mbar_wait(smem_u32(&wf[ws]), 0); tc_fence_after(); }   // loaded once, stays
                     } else {
                         ws = lwit % wr;
-                        mbar_wait(smem_u32(&wf[ws]), (uint32_t)((lwit / wr) & 1));
-                        tc_fence_after();
+                        if (!L.cat || !(t & 1)) {
+                            mbar_wait(smem_u32(&wf[ws]), (uint32_t)((lwit / wr) & 1));
+                            tc_fence_after();
+                        }
                     }
                     const uint32_t wimg = (smem_u32(Wp + (size_t)ws * w_stage) >> 4) + (L.cat ? (uint32_t)(t & 1) * 4u : 0u);
                     const uint32_t arow = aimg + (uint32_t)(a.tap_off[t] - a.min_off) * 8u;      // rows * 128 B >> 4
@@ -269,6 +274,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                                 tc_mma_bf16(dcol, dah, dw, L.idesc2, (kb | t | ks) ? 1u : 0u);   // [hi*hi | hi*lo]
                                 tc_mma_bf16(dcol, dal, dw, L.idesc, 1u);                          // lo*hi -> first nt columns
                             }
+                            if (!L.resident && pair_done) tc_commit(smem_u32(&we[ws]));
                         }
                     } else if (elect_one()) {
 #pragma unroll
@@ -284,6 +290,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                         if (!L.resident) tc_commit(smem_u32(&we[ws]));   // slot reusable once these MMAs retire
                     }
                     __syncwarp();
+                    if (pair_done) lwit++;
                 }
                 if (elect_one()) tc_commit(smem_u32(&a_empty[p * TC_MAX_ASTAGES + as]));
                 __syncwarp();
@@ -297,10 +304,11 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
         // ===================== weight producer of pipeline p = warp - 2 =====================
         const int p = warp - 2;
         // a stage is one image, or the `nt`-row part of an image that is `wnt` rows tall (see TcLaunch::wnt)
-        const size_t w_image = (size_t)L.wnt * 128u;
+        const size_t w_image = (size_t)L.wnt * (L.cat ? 256u : 128u);
+        const int nstream = L.cat ? wper : per_tile;             // streamed stages per tile
         auto w_image0 = [&](int n_tile) {
             const int vf = L.wnt / L.nt;
-            return reinterpret_cast<const uint8_t*>(a.wtc) + (size_t)(n_tile / vf) * per_tile * w_image + (size_t)(n_tile % vf) * w_stage;
+            return reinterpret_cast<const uint8_t*>(a.wtc) + (size_t)(n_tile / vf) * nstream * w_image + (size_t)(n_tile % vf) * w_stage;
         };
         {
         if (lane == 0) {
@@ -318,7 +326,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                     int lwit = 0;
                     for (int tl = 0; tl < my_tiles; tl += 2) {
                         const uint8_t* wsrc = w_image0(tile_n(tl));
-                        for (int i = 0; i < per_tile; i++, lwit++) {
+                        for (int i = 0; i < nstream; i++, lwit++) {
                             const int ws = lwit % wr;
                             mbar_wait(smem_u32(&w_empty[ws]), (uint32_t)(((lwit / wr) & 1) ^ 1));
                             mbar_expect_tx(smem_u32(&w_full[ws]), w_stage);
@@ -333,7 +341,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc_kernel(const ConvArgs 
                 int lwit = 0;
                 for (int tl = p; tl < my_tiles; tl += 2) {
                     const uint8_t* wsrc = w_image0(tile_n(tl));
-                    for (int i = 0; i < per_tile; i++, lwit++) {
+                    for (int i = 0; i < nstream; i++, lwit++) {
                         const int ws = lwit % L.ws;
                         mbar_wait(smem_u32(&we[ws]), (uint32_t)(((lwit / L.ws) & 1) ^ 1));
                         mbar_expect_tx(smem_u32(&wf[ws]), w_stage);
@@ -748,22 +756,34 @@ bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem, bool allow_tma_st = true
     //  one weight stream for nothing -- C1 flow 0.90 -> 1.00 ms)
     L.pairs = (!L.resident && L.ntiles_m * L.ntiles_n >= 2 * tc_num_sms() && !SB_ENV_ONCE("SB200_TC_NOPAIRS")) ? 1 : 0;
     const int wper_cat = (a.cin / 32) * ((a.ntaps + 1) / 2);
-    if (a.wcat && L.tma_st && L.nt <= 64 && L.resident && wper_cat * 2 * w_stage + 4 * a_buf + bar_bytes <= budget && !SB_ENV_ONCE("SB200_TC_NOCAT")) {
+    // cat mode: with resident weights when the (larger) cat images still fit; with streamed weights always (a stage is then
+    // a tap PAIR; SB200_TC_NOCATSTREAM keeps those layers on three MMAs per step)
+    if (a.wcat && L.tma_st && L.nt <= 64 && !SB_ENV_ONCE("SB200_TC_NOCAT") &&
+        (L.resident ? wper_cat * 2 * w_stage + 4 * a_buf + bar_bytes <= budget : !SB_ENV_ONCE("SB200_TC_NOCATSTREAM"))) {
         L.cat = 1; L.accw = 2 * L.nt;
         L.idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * L.nt) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     }
-    L.tmem_cols = 32;
-    while (L.tmem_cols < 4 * L.accw) L.tmem_cols <<= 1;
-    L.ws = L.resident ? (L.cat ? wper_cat : per_tile) : (per_tile < 4 ? per_tile : 4);
-    if (!L.resident && L.ws < 2) L.ws = 2;
     auto total = [&]() { return (size_t)2 * L.na * a_buf + (size_t)(L.resident ? L.ws : 2 * L.ws) * w_stage * (L.cat ? 2 : 1) + bar_bytes; };
-    L.na = TC_MAX_ASTAGES;
-    { const char* e = SB_ENV_ONCE("SB200_TC_NA"); if (e) L.na = atoi(e); }     // tuning knob
-    // (Giving the activation ring priority over a streamed weight ring -- na = 4 / ws = 2 instead of na = 2 / ws = 4 --
-    //  was measured: flow -1.5 %, 128-channel ResBlocks +3.5 %, 64-channel k = 11 layers +9 %: not adopted.)
-    while (L.na > 2 && total() > budget) L.na--;
-    while (!L.resident && L.ws > 2 && total() > budget) L.ws--;
-    if (total() > budget) return false;
+    // ring depths for the current (resident, cat) choice; false when even the minimum does not fit
+    auto fit = [&]() {
+        L.tmem_cols = 32;
+        while (L.tmem_cols < 4 * L.accw) L.tmem_cols <<= 1;
+        const int nstream = L.cat ? wper_cat : per_tile;
+        L.ws = L.resident ? nstream : (nstream < 4 ? nstream : 4);
+        if (!L.resident && L.ws < 2) L.ws = 2;
+        L.na = TC_MAX_ASTAGES;
+        { const char* e = SB_ENV_ONCE("SB200_TC_NA"); if (e) L.na = atoi(e); }     // tuning knob
+        // (Giving the activation ring priority over a streamed weight ring -- na = 4 / ws = 2 instead of na = 2 / ws = 4 --
+        //  was measured: flow -1.5 %, 128-channel ResBlocks +3.5 %, 64-channel k = 11 layers +9 %: not adopted.)
+        while (L.na > 2 && total() > budget) L.na--;
+        while (!L.resident && L.ws > 2 && total() > budget) L.ws--;
+        return total() <= budget;
+    };
+    if (!fit()) {
+        if (!(L.cat && !L.resident)) return false;
+        L.cat = 0; L.accw = L.nt; L.idesc2 = 0;          // the doubled stages of a streamed cat ring do not fit: three MMAs per step
+        if (!fit()) return false;
+    }
     L.depth = L.na - 1;
     { const char* e = SB_ENV_ONCE("SB200_TC_DEPTH"); if (e && atoi(e) >= 1 && atoi(e) < L.na) L.depth = atoi(e); }
     smem = total() + 2048;
