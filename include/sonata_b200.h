@@ -74,6 +74,8 @@ int32_t sb200_device_count(void);
  * (where the reference opens `<voice>.onnx`).  `device` = CUDA ordinal; -1 loads the config only
  * (host-side queries and id mapping work, every synthesis call fails with OPERATION_ERROR). */
 int32_t sb200_voice_load(const char* config_path, int32_t device, sb200_voice** out, sb200_error* err);
+/* Drops the caller's handle.  Jobs and latents created from the voice share ownership of it (the reference holds the
+ * model behind an Arc, capi/src/lib.rs:314,375): they stay valid and may be freed afterwards, in any order. */
 void sb200_voice_free(sb200_voice* v);
 
 /* SonataModel::audio_output_info (core/src/lib.rs:83) */
