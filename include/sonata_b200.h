@@ -181,6 +181,13 @@ int32_t sb200_job_profile(const sb200_job* job, sb200_region_stat* out, int32_t 
 /* one convolution on caller data through either backend (kernel unit tests):
  * y[rows][cout] (=|+=) scale * (act(bias + conv_k,dil(lrelu_slope(x))) + res); w is [cout][cin][k];
  * act 0 none, 1 relu, 2 tanh*sigmoid gate (y is [rows][cout/2]); rows >= valid_rows are masked. */
+/* Test hook: the launch configuration the planner of backend 1 (tcgen05 bf16x2 conv) / 2 (tcgen05 3xTF32 conv) would choose
+ * for one convolution of `rows` output rows -- nothing is allocated or launched, so it also works without a GPU.
+ * out16, backend 1: {nt, image rows, m-tiles, n-tiles, resident, cat, tma_epilogue, pairs, act. stages, weight stages,
+ * staging tiles, smem bytes, tma_in, v8, tmem columns, window rows}; backend 2: {nth, image rows, m-pairs, n-tiles, act.
+ * stages, weight stages, chunk K-blocks, smem bytes, tmem columns, window rows, 0...}.  Returns 0, or 19 if unsupported. */
+int32_t sb200_debug_plan(int32_t backend, int64_t rows, int32_t cin, int32_t cout, int32_t k, int32_t dil, int32_t act,
+                         int32_t has_res, int32_t accumulate, int32_t* out16);
 int32_t sb200_debug_conv(int32_t device, int32_t backend, const float* x, int32_t rows, int32_t cin, const float* w,
                          const float* bias, int32_t cout, int32_t k, int32_t dil, float in_slope, int32_t act,
                          const float* res, float scale, int32_t accumulate, float* y, int32_t valid_rows,

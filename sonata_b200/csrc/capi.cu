@@ -3,6 +3,7 @@
 // no exception crosses the ABI; failures become {code, heap message}.
 #include "../../include/sonata_b200.h"
 #include "engine.h"
+#include "tc_common.cuh"
 #include <chrono>
 #include <cstring>
 #include <deque>
@@ -385,6 +386,33 @@ int32_t sb200_job_profile(const sb200_job* job, sb200_region_stat* out, int32_t 
     }
     return n;
 }
+int32_t sb200_debug_plan(int32_t backend, int64_t rows, int32_t cin, int32_t cout, int32_t k, int32_t dil, int32_t act,
+                         int32_t has_res, int32_t accumulate, int32_t* out16) {
+    // Planning only: nothing is allocated or launched, so this also runs where there is no GPU (host-logic tests); tensor
+    // maps are assumed available, as on any sm_90+ driver.  Buffers are described by stand-in addresses (the planners look
+    // at alignment only).  Layer conventions as in sb200_debug_conv / the engine's ResBlock and flow layers.
+    if (!out16 || cin <= 0 || cout <= 0 || k <= 0 || k > SB_MAX_TAPS || dil <= 0 || rows <= 0) return 19;
+    static float anchor[64];
+    float* const stand_in = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(anchor) + 127) & ~(uintptr_t)127);
+    ConvArgs p{};
+    const int R = (int)((rows + 255) / 256 * 256);
+    const int ycols = act == ACT_GATE ? cout / 2 : cout;
+    p.x = stand_in; p.ldx = cin; p.rows_in = R; p.cin = cin; p.in_slope = 0.1f;
+    p.w = stand_in; p.bias = stand_in; p.ldw = cout; p.cout = cout;
+    p.tc_nt = cout <= 128 ? cout : (cout % 128 == 0 ? 128 : (cout % 96 == 0 ? 96 : 0));      // voice.cu tc_tile_for
+    p.wtc = p.tc_nt ? stand_in : nullptr; p.wcat = (p.tc_nt && p.tc_nt <= 64) ? stand_in : nullptr; p.wtf = stand_in;
+    p.ntaps = k;
+    for (int t = 0; t < k; t++) p.tap_off[t] = (t - (k - 1) / 2) * dil;
+    p.min_off = p.tap_off[0]; p.span = (k - 1) * dil;
+    p.rows_q = R; p.orow_mul = 1; p.orow_add = 0;
+    p.act = act; p.scale = 1.f; p.res = has_res ? stand_in : nullptr; p.ldres = cout;
+    p.y0 = stand_in; p.ldy0 = ycols; p.acc0 = accumulate; p.split = cout; p.y1 = stand_in; p.ldy1 = ycols; p.acc1 = accumulate;
+    plan_assume_tensor_maps() = true;
+    const bool ok = backend == 2 ? conv_tf_plan_info(p, out16) : conv_tc_plan_info(p, out16);
+    plan_assume_tensor_maps() = false;
+    return ok ? 0 : 19;
+}
+
 int32_t sb200_debug_conv(int32_t device, int32_t backend, const float* x, int32_t rows, int32_t cin, const float* w,
                          const float* bias, int32_t cout, int32_t k, int32_t dil, float in_slope, int32_t act,
                          const float* res, float scale, int32_t accumulate, float* y, int32_t valid_rows,

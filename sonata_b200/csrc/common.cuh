@@ -128,6 +128,7 @@ inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
 void launch_conv_simt(const ConvArgs& a, cudaStream_t st);
 int conv_simt_bn_for(int cout);
 bool conv_tc_supported(const ConvArgs& a);
+bool conv_tc_plan_info(const ConvArgs& a, int* out16);     // planning only, see sb200_debug_plan
 void launch_conv_tc(const ConvArgs& a, cudaStream_t st);
 bool try_launch_conv_tc(const ConvArgs& a, cudaStream_t st);
 size_t conv_tc_weight_floats(int cin, int cout, int ntaps, int nt);
@@ -135,6 +136,7 @@ void conv_tc_build_weights(const float* wt, int ldw, int cin, int cout, int ntap
 size_t conv_tc_cat_weight_floats(int cin, int cout, int ntaps, int nt);
 void conv_tc_build_weights_cat(const float* wt, int ldw, int cin, int cout, int ntaps, int nt, float* out);
 bool conv_tf_supported(const ConvArgs& a);
+bool conv_tf_plan_info(const ConvArgs& a, int* out16);
 void launch_conv_tf(const ConvArgs& a, cudaStream_t st);
 bool try_launch_conv_tf(const ConvArgs& a, cudaStream_t st);
 size_t conv_tf_weight_floats(int cin, int cout, int ntaps);

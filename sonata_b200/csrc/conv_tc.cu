@@ -721,7 +721,7 @@ bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem, bool allow_tma_st = true
     int tmast_maxc = 64;
     { const char* e = SB_ENV_ONCE("SB200_TC_TMAST_MAXC"); if (e) tmast_maxc = atoi(e); }
     L.tma_st = (allow_tma_st && L.v8 && (a.cout == 32 || a.cout == 64 || a.cout == 128) && a.cout <= tmast_maxc && L.nt == a.cout &&
-                a.act != ACT_GATE && !a.phase_cols && a.split >= a.cout && a.orow_mul == 1 && tensor_map_encoder() != nullptr &&
+                a.act != ACT_GATE && !a.phase_cols && a.split >= a.cout && a.orow_mul == 1 && have_tensor_maps() &&
                 !SB_ENV_ONCE("SB200_TC_NOTMAST")) ? 1 : 0;
     if (a.res && (a.ldres & 3)) L.tma_st = 0;
     L.nstg = a.acc0 ? 2 : 1;
@@ -748,7 +748,7 @@ bool plan(const ConvArgs& a, TcLaunch& L, size_t& smem, bool allow_tma_st = true
     const size_t budget = 225 * 1024 - 2048;
     const size_t bar_bytes = (2 * TC_MAX_WRING + 6 * TC_MAX_ASTAGES + 12) * 8 + 16 + (L.tma_st ? 2 * L.nstg * TC_OUT_BYTES : 0);
     L.bulk_in = (SB_ENV_ONCE("SB200_TC_NOBULKIN") == nullptr && a.ldx == 32 && a.cin == 32) ? 1 : 0;
-    L.tma_in = (tensor_map_encoder() != nullptr && L.win <= 256 && (a.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0 &&
+    L.tma_in = (have_tensor_maps() && L.win <= 256 && (a.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0 &&
                 !SB_ENV_ONCE("SB200_TC_NOTMAIN")) ? 1 : 0;
     L.resident = (L.ntiles_n == 1 && per_tile <= TC_MAX_WRING && per_tile * w_stage + 4 * a_buf + bar_bytes <= budget) ? 1 : 0;
     if (L.tma_st && !L.resident && SB_ENV_ONCE("SB200_TC_TMAST_RESONLY")) return plan(a, L, smem, false);
@@ -831,6 +831,16 @@ bool tensor_map_2d(CUtensorMap* tm, const void* base, unsigned long long cols, u
         return false;
     if (cache.size() > 4096) cache.clear();
     cache.emplace(key, *tm);
+    return true;
+}
+
+// planning only (no launch): the configuration the launcher would choose; see sb200_debug_plan
+bool conv_tc_plan_info(const ConvArgs& a, int* out) {
+    TcLaunch L{}; size_t smem = 0;
+    if (a.cin % 32 || a.cout % 32 || a.ntaps > SB_MAX_TAPS || !plan(a, L, smem)) return false;
+    const int v[16] = {L.nt, L.wnt, L.ntiles_m, L.ntiles_n, L.resident, L.cat, L.tma_st, L.pairs, L.na, L.ws, L.nstg, (int)smem,
+                       L.tma_in, L.v8, L.tmem_cols, L.win};
+    for (int i = 0; i < 16; i++) out[i] = v[i];
     return true;
 }
 

@@ -438,7 +438,7 @@ constexpr size_t TF_SMEM_BUDGET = 227 * 1024 - 1024;     // opt-in maximum minus
 bool plan(const ConvArgs& a, TfLaunch& L, size_t& smem) {
     if (!a.wtf || a.cin % 32 || a.cout % 32 || a.ntaps < 1 || a.ntaps > SB_MAX_TAPS) return false;
     if (a.act == ACT_GATE || a.split < a.cout || a.orow_mul != 1 || a.phase_cols) return false;
-    if (!tensor_map_encoder()) return false;
+    if (!have_tensor_maps()) return false;
     auto al32 = [](const void* p, int ld) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 31) == 0 && (ld & 7) == 0); };
     if (!al32(a.y0, a.ldy0) || !al32(a.res, a.ldres)) return false;
     if ((a.ldx & 3) || (reinterpret_cast<uintptr_t>(a.x) & 15)) return false;
@@ -492,6 +492,15 @@ uint32_t tf32_rn_host(float f) {        // round to nearest, ties away from zero
 
 }  // namespace
 
+// planning only (no launch): the configuration the launcher would choose; see sb200_debug_plan
+bool conv_tf_plan_info(const ConvArgs& a, int* out) {
+    TfLaunch L{}; size_t smem = 0;
+    if (!plan(a, L, smem)) return false;
+    const int v[16] = {L.nth, L.wnth, L.ntiles_mp, L.ntiles_n, L.na, L.nw, L.chunk_kb, (int)smem, L.tmem_cols, L.win, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 16; i++) out[i] = v[i];
+    return true;
+}
+
 bool conv_tf_supported(const ConvArgs& a) {
     TfLaunch L; size_t smem;
     return plan(a, L, smem);
@@ -522,7 +531,7 @@ bool try_launch_conv_tf(const ConvArgs& a, cudaStream_t st) {
 }
 
 bool gemm_tf_supported(const TfGemm& g) {
-    if (!tensor_map_encoder()) return false;
+    if (!have_tensor_maps()) return false;
     if (g.nth != 96 && g.nth != 64 && g.nth != 32) return false;
     auto al = [](const void* p, int ld, int a) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0 && (ld & 3) == 0); };
     return al(g.a, g.lda, 16) && al(g.b, g.ldb, 16) && al(g.y, g.ldy, 32) && (g.ldy & 7) == 0 && al(g.res, g.ldy, 32);

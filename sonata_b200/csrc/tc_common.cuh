@@ -190,6 +190,11 @@ inline TensorMapEncodeFn tensor_map_encoder() {
     return fn;
 }
 
+// The launch planners only ask WHETHER tensor maps can be built.  sb200_debug_plan (host-logic tests on machines without a
+// driver) sets this to plan as a B200 box would; nothing is launched on that path.
+inline bool& plan_assume_tensor_maps() { static bool v = false; return v; }
+inline bool have_tensor_maps() { return plan_assume_tensor_maps() || tensor_map_encoder() != nullptr; }
+
 // 2-D fp32 tensor map [rows][cols] (row stride ld floats), box = box_cols x box_rows, zero fill outside the array.
 // Encoding costs ~1-2 us on the host and the same few (buffer, shape) combinations recur launch after launch (the
 // arena hands out the same addresses for the same batch shape), so the encoded maps are cached per host thread.
