@@ -29,7 +29,8 @@ Second opinion (what this restatement IS checked against): Hugging Face ``transf
 independent implementation of the published VITS network, not derived from Piper and not written here -- loaded with
 the same synthetic high-quality (ResBlock1, en_US-ryan-high architecture) voice reproduces this oracle's waveform to
 2e-6 .. 4e-6, frame counts identical, on the deterministic AND the stochastic path (``tests/hf_reference.py``,
-``tests/test_hf_pin.py``, fixtures + generator under ``tests/golden/hf/``); the medium voice agrees with it up to the
+``tests/test_hf_pin.py``, fixtures + generator under ``tests/golden/hf/``), multi-speaker conditioning included (3-speaker
+voice, ``speaker_id``); the medium voice agrees with it up to the
 vocoder input (``z`` within 5e-5).  Not covered by it: the ResBlock2 wiring of the medium voices' vocoder (transformers
 implements ResBlock1 only) and anything Piper's ONNX export may do differently from the published model code.
 

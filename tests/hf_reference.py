@@ -21,8 +21,10 @@ import math
 import numpy as np
 import torch
 
+GIN_CHANNELS = 512      # Piper multi-speaker voices (sonata_b200.voicegen.GIN_CHANNELS)
 
-def build_hf_model(a: dict, decoder: bool = True):
+
+def build_hf_model(a: dict, decoder: bool = True, n_speakers: int = 1):
     """`a`: an architecture dict of sonata_b200.voicegen.ARCH.  decoder=False builds a throw-away one-stage vocoder so that
     voices whose HiFi-GAN transformers cannot express (ResBlock2: the medium voices) can still be compared on everything
     in front of it through `VitsModelOutput.spectrogram` (= the flow output z)."""
@@ -35,7 +37,8 @@ def build_hf_model(a: dict, decoder: bool = True):
         vocab_size=a["n_vocab"], hidden_size=a["hidden"], num_hidden_layers=a["layers"],
         num_attention_heads=a["heads"], window_size=a["window"], use_bias=True, ffn_dim=a["filter"],
         ffn_kernel_size=a["kernel"], flow_size=a["inter"], hidden_act="relu", layerdrop=0.0,
-        use_stochastic_duration_prediction=True, num_speakers=1,
+        use_stochastic_duration_prediction=True, num_speakers=n_speakers,
+        speaker_embedding_size=GIN_CHANNELS if n_speakers > 1 else 0,
         upsample_initial_channel=a["up_init"], upsample_rates=list(a["up_rates"]),
         upsample_kernel_sizes=list(a["up_kernels"]), resblock_kernel_sizes=list(a["res_kernels"]),
         resblock_dilation_sizes=[list(d) for d in a["res_dils"]], leaky_relu_slope=0.1,
@@ -117,6 +120,15 @@ def load_piper_tensors(model, T: dict, a: dict, decoder: bool = True):
             _set(fl.wavenet.res_skip_layers[l].bias, T[p + f"enc.res_skip_layers.{l}.bias"])
         _set(fl.conv_post.weight, T[p + "post.weight"]); _set(fl.conv_post.bias, T[p + "post.bias"])
 
+    if "emb_g.weight" in T:
+        # multi-speaker voices: g = emb_g(sid) enters through 1x1 convs in the duration predictor, every WaveNet and the vocoder
+        _set(model.embed_speaker.weight, T["emb_g.weight"])
+        _set(dp.cond.weight, T["dp.cond.weight"]); _set(dp.cond.bias, T["dp.cond.bias"])
+        for f, fl in enumerate(model.flow.flows):
+            p = f"flow.flows.{2 * f}.enc.cond_layer."
+            _set_weight_normed(fl.wavenet.cond_layer, T[p + "weight"]); _set(fl.wavenet.cond_layer.bias, T[p + "bias"])
+        if decoder:
+            _set(model.decoder.cond.weight, T["dec.cond.weight"]); _set(model.decoder.cond.bias, T["dec.cond.bias"])
     if not decoder:
         return model
     dec = model.decoder
@@ -134,7 +146,7 @@ def load_piper_tensors(model, T: dict, a: dict, decoder: bool = True):
     return model
 
 
-def hf_infer(model, ids, noise_scale: float, length_scale: float, noise_w: float, seed: int = 0):
+def hf_infer(model, ids, noise_scale: float, length_scale: float, noise_w: float, seed: int = 0, speaker_id=None):
     """Runs `VitsModel.forward` itself.  Returns (waveform f32[n], eps_w f32[2, T], eps_z f32[inter, frames]): the two
     Gaussian draws the forward made (duration-predictor latents first, then `randn_like(prior_means)`), re-drawn from
     the same generator state so that another implementation can be fed the identical noise."""
@@ -144,7 +156,7 @@ def hf_infer(model, ids, noise_scale: float, length_scale: float, noise_w: float
     model.speaking_rate = 1.0 / float(length_scale)
     torch.manual_seed(seed)
     with torch.no_grad():
-        out = model(input_ids=ids, attention_mask=torch.ones_like(ids))
+        out = model(input_ids=ids, attention_mask=torch.ones_like(ids), speaker_id=speaker_id)
     wav = out.waveform[0].float().numpy().copy()
     hf_infer.last_spectrogram = out.spectrogram[0].float().numpy().copy()      # [inter, frames]: the flow output z
     frames = wav.shape[0] // int(np.prod(model.config.upsample_rates))

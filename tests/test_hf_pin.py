@@ -97,6 +97,27 @@ def test_medium_voice_up_to_the_vocoder_against_live_transformers_run(oracle_wei
         assert float(np.abs(z - z_hf).max()) < 5e-5, scales                    # z is O(1..5)
 
 
+def test_multi_speaker_conditioning_against_live_transformers_run():
+    """The N1 row: `sid` -> emb_g -> 1x1 conditioning convs in the duration predictor, all four WaveNets and the vocoder
+    input (piper/src/lib.rs:353-358), on a 3-speaker high voice, two speakers, stochastic path."""
+    pytest.importorskip("transformers")
+    import hf_reference as hf
+    a = voicegen.ARCH["high"]
+    T = voicegen.make_tensors("high", n_speakers=3)
+    m = hf.load_piper_tensors(hf.build_hf_model(a, n_speakers=3), T, a)
+    W = vo.to_torch(T)
+    ids = vo.synthetic_ids(16, utt=11)
+    outs = []
+    for sid, scales, seed in ((0, (0.667, 1.0, 0.8), 2), (2, (0.667, 1.0, 0.8), 2), (2, (0.0, 1.0, 0.0), 0)):
+        wav, ew, ez = hf.hf_infer(m, ids, *scales, seed=seed, speaker_id=sid)
+        got = vo.infer(W, ids, list(scales), eps_w=ew[None] if scales[2] else None, eps_z=ez[None] if scales[0] else None,
+                       sid=sid).numpy()
+        assert got.shape == wav.shape, (sid, got.shape, wav.shape)
+        assert float(np.abs(got - wav).max()) < TOL_ORACLE, sid
+        outs.append(wav)
+    assert outs[0].shape != outs[1].shape or float(np.abs(outs[0] - outs[1]).max()) > 1e-2      # the speaker matters
+
+
 # ------------------------------------------------------------------------------------------------ CUDA path
 def _run_cuda(m, ids, scales, eps_w, eps_z):
     from sonata_b200.job import SynthesisJob
