@@ -42,16 +42,6 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
                                                                          // warp sleeps in hardware instead of spinning
     return ok != 0;
 }
-// non-blocking phase test (a thread that polls several barriers must not sleep on one of them)
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     unsigned spins = 0;
     unsigned long long t0 = 0;
